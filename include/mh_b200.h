@@ -1,0 +1,188 @@
+/* mh_b200.h -- C ABI of the B200-native MelHuBERT hot path (libmh_b200.so).
+ *
+ * Every entry point takes plain device pointers + sizes and a cudaStream_t (passed as void*);
+ * PyTorch (or any other host) owns all memory.  Return value: 0 on success, non-zero on error
+ * with a thread-local message available from mh_last_error().  There is no CPU fallback.
+ *
+ * Each function names the reference code it replaces (paths relative to the reference root,
+ * dlion168/Speech-SSL-Compression).  Activations are bf16, row-major, one row per frame in
+ * (batch, time) order; master weights / gradients / statistics are fp32.
+ */
+#ifndef MH_B200_H
+#define MH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* mh_last_error(void);
+int mh_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long mh_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * GEMM on tcgen05/TMEM fed by TMA:  D[M,N] = A[M,K] * B[N,K]^T  (+ epilogue)
+ * Replaces torch._C._nn.linear at pytorch_code/forward_multihead_attention.py:71-76,110,233
+ * (q/k/v/out projections), module.py:126-129 (fc1/fc2), model.py:109-110,148 (pre/final
+ * projections) and their autograd dgrad / wgrad.
+ *   a_mn = 0: A stored [M][K] (K contiguous, leading dim lda);  a_mn = 1: stored [K][M].
+ *   b_mn = 0: B stored [N][K];                                   b_mn = 1: stored [K][N].
+ * All leading dimensions are in elements and must be multiples of 8; pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+enum {
+  MH_EPI_BF16 = 0,  /* D(bf16) = acc [+ bias[n]]                                              */
+  MH_EPI_GELU = 1,  /* pre = bf16(acc + bias); aux_out = pre (if given); D = dropout(gelu(pre)) */
+  MH_EPI_RES = 2,   /* D(bf16) = dropout(acc + bias) + aux_in[m,n]                             */
+  MH_EPI_F32 = 3,   /* D(f32) += acc * (mask ? mask[m,n] : 1)   (atomic; split-K capable)      */
+  MH_EPI_DGELU = 4, /* D(bf16) = acc * dropout_keep_scale * gelu'(aux_in[m,n])                 */
+  MH_EPI_ADD = 5    /* D(bf16) = acc + aux_in[m,n]                                             */
+};
+
+typedef struct {
+  int M, N, K;
+  const void* A; long long lda; int a_mn;
+  const void* B; long long ldb; int b_mn;
+  void* D; long long ldd;
+  int epilogue;
+  const float* bias;         /* [N] or NULL */
+  const void* aux_in;        /* bf16 [M, ld_aux] */
+  void* aux_out;             /* bf16 [M, ld_aux] */
+  long long ld_aux;
+  const uint8_t* mask;       /* MH_EPI_F32: 0/1 bytes [M, ldd] or NULL */
+  float p_drop; uint64_t seed; uint32_t site;   /* dropout stream (see mh_common.cuh) */
+  int block_n;               /* 0 = auto, else 128 or 256 */
+  int split_k;               /* 0 = auto (MH_EPI_F32 only), else number of K splits */
+} mh_gemm_args;
+
+int mh_gemm(const mh_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-head attention (flash style, no T x T tensor in HBM).
+ * Replaces pytorch_code/forward_multihead_attention.py:39-69 (_scaled_dot_product_attention)
+ * and the reshapes at :199-201, :231.
+ *   qkv : bf16 [B*T, 3*E] rows = frames, columns = [q | k | v], E = 64 * heads
+ *   kv_len[b] : number of valid (non padded) keys of batch element b (suffix padding)
+ *   out : bf16 [B*T, E]      lse : f32 [B, heads, T] (log-sum-exp of the scaled scores)
+ *   dropout on the probabilities regenerated from (seed, site) in the backward.
+ * ------------------------------------------------------------------------------------- */
+int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, int B, int T, int heads,
+                int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* dqkv : bf16 [B*T, 3*E];  delta : f32 scratch [B, heads, T] */
+int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                float* delta, void* dqkv, int B, int T, int heads, int causal, float p_drop, uint64_t seed,
+                uint32_t site, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LayerNorm family (module.py:121-123,129-131,232-236: dropout -> +residual -> LayerNorm is
+ * split as GEMM epilogue (dropout, +residual) + this kernel).
+ *   y = LN(x) * gamma + beta, eps; stats (mean, rstd) saved for the backward.
+ *   optional dropout on the output (encoder-level F.dropout, module.py:236).
+ * ------------------------------------------------------------------------------------- */
+int mh_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int rows, int cols, float eps, float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* dx (bf16) = LN backward of dy (+ dres if given);  dgamma/dbeta (f32 [cols]) are accumulated. */
+int mh_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, float p_drop,
+                     uint64_t seed, uint32_t site, void* stream);
+
+/* column sums: out[n] += sum_m x[m, n]  (bias gradients).  x bf16 [rows, ld] */
+int mh_colsum(const void* x, long long ld, float* out, int rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Weight preparation W0: fp32 master (+ optional bool mask) -> bf16 operand, optionally also
+ * its transpose (for dgrad).  Replaces the per-forward prune hook
+ * pytorch_code/prune.py:24-38,64-85 (weight_orig.masked_fill(~mask, 0)) x 144 tensors and the
+ * autocast casts.
+ *   src f32 [rows, cols]; mask u8 [rows, cols] or NULL; dst bf16 [rows, ld_dst];
+ *   dst_t bf16 [cols, ld_dst_t] or NULL.
+ * ------------------------------------------------------------------------------------- */
+int mh_weight_prep(const float* src, const uint8_t* mask, void* dst, long long ld_dst, void* dst_t,
+                   long long ld_dst_t, int rows, int cols, void* stream);
+/* f32 vector (+mask) -> f32 vector (bias prep: masked_fill) */
+int mh_bias_prep(const float* src, const uint8_t* mask, float* dst, int n, void* stream);
+/* generic casts */
+int mh_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+int mh_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Input masking + padding (model.py:80 x[mask_indices] = 0; module.py:226-227 x[pad] = 0):
+ *   dst(bf16)[r, :] = zero[r] ? 0 : src(f32)[r, :]
+ * ------------------------------------------------------------------------------------- */
+int mh_mask_rows_f32_to_bf16(const float* src, const uint8_t* zero_row, void* dst, int rows, int cols,
+                             void* stream);
+int mh_zero_rows_bf16(void* x, const uint8_t* zero_row, int rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Masked-frame selection (model.py:147-150): index list of rows with sel[r] != 0 in row-major
+ * (b, t) order, count written to *count (device).  idx has room for `rows` entries; unused
+ * tail entries are set to -1.
+ * ------------------------------------------------------------------------------------- */
+int mh_select_rows(const uint8_t* sel, int* idx, int* count, int rows, void* stream);
+/* dst[i, :] = src[idx[i], :] for i < n_idx (idx[i] < 0 -> zeros) */
+int mh_gather_rows(const void* src, const int* idx, void* dst, int n_idx, int cols, void* stream);
+/* dst[idx[i], :] += src[i, :]  (backward of the gather; rows are unique) */
+int mh_scatter_rows_add(const void* src, const int* idx, void* dst, int n_idx, int cols, void* stream);
+int mh_gather_labels(const long long* label, const int* idx, long long* dst, int n_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Criteria.
+ * CE (upstream/melhubert/pretrain_expert.py:25,116-117): CrossEntropyLoss(ignore_index=-100,
+ * mean) fused forward + backward over bf16 logits [n_rows, n_class].
+ *   acc[0] += sum of row losses, acc[1] += number of non-ignored rows;
+ *   dlogits (bf16) = (softmax - onehot) * grad_scale[0]   (grad_scale lives on the device so
+ *   that the global-mean normaliser can come from an all-reduce without a host sync).
+ *   Rows >= *n_valid (device, optional) are ignored.
+ * ------------------------------------------------------------------------------------- */
+int mh_ce_fwd(const void* logits, const long long* labels, const int* n_valid, float* row_loss, float* acc,
+              int n_rows, int n_class, void* stream);
+int mh_ce_bwd(const void* logits, const long long* labels, const int* n_valid, const float* grad_scale,
+              void* dlogits, int n_rows, int n_class, void* stream);
+/* KD (distillation/pretrain_expert.py:83-92): hard = CE(student), soft = KL(softmax(t/T) ||
+ * softmax(s/T)) summed over rows; acc[0] += sum CE_s, acc[1] += count, acc[2] += sum KL,
+ * acc[3] += sum CE_t, acc[4] += rows.  Backward: dlogits = w_hard[0]*(p_s - onehot) +
+ * w_soft[0]*(p_sT - p_tT)/T with device-side weights. */
+int mh_kd_fwd(const void* s_logits, const void* t_logits, const long long* labels, const int* n_valid, float T,
+              float* acc, int n_rows, int n_class, void* stream);
+int mh_kd_bwd(const void* s_logits, const void* t_logits, const long long* labels, const int* n_valid, float T,
+              const float* w_hard, const float* w_soft, void* dlogits, int n_rows, int n_class, void* stream);
+/* L1 + cosine per-frame criterion (north_star; DistilHuBERT form):
+ *   acc[0] += sum |p - t|, acc[1] += sum -logsigmoid(cos(p, t));  rows of `cols` bf16.
+ *   backward: dpred = w_l1[0]*sign(p - t) + w_cos[0]*d(-logsigmoid(cos))/dp */
+int mh_l1cos_fwd(const void* pred, const void* target, float* acc, int rows, int cols, void* stream);
+int mh_l1cos_bwd(const void* pred, const void* target, const float* w_l1, const float* w_cos, void* dpred,
+                 int rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pruning objects.
+ * Global magnitude threshold (pytorch_code/prune.py:553-573 topk(k, largest=False) over the
+ * concatenation of all prunable tensors): exact k-th smallest |w| by 4-pass radix select over
+ * the fp32 bit patterns.  ptrs/sizes describe the tensors (device array of device pointers).
+ *   result[0] = threshold bits, result[1] = #elements strictly below, result[2] = #equal.
+ * mh_apply_threshold_mask then clears mask bytes: |w| < thr always; |w| == thr for the first
+ * `n_ties` elements in flat order ("lowest flat index wins").
+ * ------------------------------------------------------------------------------------- */
+int mh_abs_kth_smallest(const float* const* ptrs, const long long* sizes, int n_tensors, long long k,
+                        unsigned long long* workspace /* >= 65536+8 u64 */, unsigned long long* result,
+                        void* stream);
+int mh_apply_threshold_mask(const float* w, uint8_t* mask, long long n, const unsigned long long* result,
+                            long long k, unsigned long long* tie_counter, void* stream);
+/* L1 scores: out[r] = sum_c |w[r, c]| for r < rows (fp64 accumulate), w f32 [rows, ld] */
+int mh_row_abs_sums(const float* w, long long ld, double* out, int rows, int cols, void* stream);
+int mh_col_abs_sums(const float* w, long long ld, double* out, int rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused Adam step (runner.py:411-427: grad /= n; clip_grad_norm_; Adam; zero_grad) over a
+ * flat fp32 parameter buffer.  sumsq: device scalar holding the global grad sum of squares
+ * (from mh_sumsq); clip applied as min(1, max_norm / (sqrt(sumsq)*grad_scale + 1e-6)).
+ * ------------------------------------------------------------------------------------- */
+int mh_sumsq(const float* x, long long n, float* out, void* stream);
+int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, const int* step /* device */, float grad_scale,
+                 float max_norm, const float* sumsq, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MH_B200_H */

@@ -1,0 +1,429 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T   bf16 x bf16 -> fp32 (TMEM) -> fused epilogue
+//
+// Roles (320 threads, one CTA per SM):
+//   warps 0-7 : epilogue.  warp w reads TMEM lanes 32*(w%4)..+31 (one accumulator row per
+//               thread) and the column half (w/4) of the tile; bias / GELU / dropout /
+//               residual / mask are applied in fp32 registers; 16-byte global stores.
+//   warp 8    : TMA producer (one elected lane): 128B-swizzled tiles of A and B into a
+//               4- or 6-stage shared-memory ring, mbarrier complete_tx signalling.
+//   warp 9    : TMEM allocator + MMA issuer (one elected lane): tcgen05.mma 128 x BN x 16,
+//               accumulators double buffered in TMEM so the epilogue of tile i overlaps the
+//               main loop of tile i+1; tcgen05.commit releases smem stages / publishes tiles.
+// Operands may be K-major (row = m or n, 64 contiguous k) or MN-major (row = k, 64 contiguous
+// m or n); the latter is what wgrad (dW = dY^T X) needs and avoids any transpose kernel.
+// MH_EPI_F32 accumulates with red.global.add.f32, which makes split-K and gradient
+// accumulation the same code path.
+#include "mh_b200.h"
+#include "mh_common.cuh"
+#include "mh_ptx.cuh"
+
+namespace mh {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int GEMM_THREADS = 320;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+struct GemmDev {
+  int M, N, K;
+  void* D;
+  long long ldd;
+  const float* bias;
+  const __nv_bfloat16* aux_in;
+  __nv_bfloat16* aux_out;
+  long long ld_aux;
+  const uint8_t* mask;
+  DropCfg drop;
+  int split_k;
+};
+
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int kblocks_total = (p.K + BK - 1) / BK;
+  const int splits = p.split_k;
+  const int kb_per_split = (kblocks_total + splits - 1) / splits;
+  const int num_tiles = num_m * num_n * splits;
+
+  if (warp == PRODUCER_WARP) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % splits;
+        const int mn = tile / splits;
+        const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kblocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full[stage], m0 + c * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, &full[stage], n0 + c * 64, kb * BK);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % splits;
+        const int mn = tile / splits;
+        const int n0 = (mn % num_n) * BN;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kblocks_total, kb0 + kb_per_split);
+        // shrink the instruction N on the ragged last column tile (multiples of 16)
+        int n_valid = min(BN, p.N - n0);
+        n_valid = (n_valid + 15) & ~15;
+        const uint32_t idesc = make_idesc_bf16(BM, n_valid, A_MN, B_MN);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_sdesc(sa + k * 2048, BK * 128, 1024) : make_sdesc(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? make_sdesc(sb + k * 2048, BK * 128, 1024) : make_sdesc(sb + k * 32, 0, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- epilogue warps
+    const int quad = warp & 3;         // TMEM lane quadrant
+    const int half = warp >> 2;        // column half of the tile
+    const int row_in_tile = quad * 32 + lane;
+    constexpr int kChunksPerHalf = BN / 64;  // 32-column chunks per half
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mn = tile / splits;
+      const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
+      const int kb0 = (tile % splits) * kb_per_split;
+      const bool has_k = kb0 < kblocks_total;  // empty split (possible when splits does not divide)
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const long long row = m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < kChunksPerHalf; ++c) {
+        const int col_in_tile = half * (BN / 2) + c * 32;
+        const int col0 = n0 + col_in_tile;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_in_tile, r);
+        tmem_ld_wait();
+        if (!row_ok || !has_k) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = col0 + q * 8;
+          if (col >= p.N) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+          if (EPI == MH_EPI_F32) {
+            float* dst = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
+            if (p.mask != nullptr) {
+              const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + row * p.ldd + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (((mk.x >> (8 * j)) & 0xFF) == 0) v[j] = 0.f;
+                if (((mk.y >> (8 * j)) & 0xFF) == 0) v[4 + j] = 0.f;
+              }
+            }
+            red_add_f32x4(dst, v[0], v[1], v[2], v[3]);
+            red_add_f32x4(dst + 4, v[4], v[5], v[6], v[7]);
+            continue;
+          }
+          if (EPI == MH_EPI_BF16 || EPI == MH_EPI_GELU || EPI == MH_EPI_RES) {
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+          }
+          if (EPI == MH_EPI_GELU) {
+            // the reference evaluates GELU in fp32 on the half-precision fc1 output
+            // (fairseq_code/gelu.py:35 under autocast): round first, then activate.
+            uint4 pre = f32_to_bf16x8(v);
+            if (p.aux_out != nullptr) stg128(p.aux_out + row * p.ld_aux + col, pre);
+            bf16x8_to_f32(pre, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (EPI == MH_EPI_DGELU) {
+            float pre[8];
+            bf16x8_to_f32(ldg128(p.aux_in + row * p.ld_aux + col), pre);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
+          }
+          if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
+            if (p.drop.thresh != 0) {
+              const uint64_t group = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + (col >> 3);
+              const uint32_t keep = drop_keep8(p.drop, group);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1) ? v[j] * p.drop.scale : 0.f;
+            }
+          }
+          if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
+            float a[8];
+            bf16x8_to_f32(ldg128(p.aux_in + row * p.ld_aux + col), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += a[j];
+          }
+          stg128(reinterpret_cast<__nv_bfloat16*>(p.D) + row * p.ldd + col, f32_to_bf16x8(v));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major array [rows][cols] (leading dim ld elements), box = {box_cols, box_rows},
+// 128-byte swizzle, out-of-bounds reads return zeros.
+int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                 int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  MH_CHECK(ld % 8 == 0, "TMA leading dimension must be a multiple of 8 elements (got %lld)", ld);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
+           static_cast<int>(r), rows, cols, ld, box_cols, box_rows);
+  return 0;
+}
+
+// 3-D variant used by attention: [d2][d1][d0] with strides in elements.
+int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
+                 long long stride2, int box0, int box1) {
+  EncodeTiledFn enc = get_encode();
+  MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  MH_CHECK(stride1 % 8 == 0 && stride2 % 8 == 0, "TMA strides must be multiples of 8 elements");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1) * 2, static_cast<cuuint64_t>(stride2) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with %d", static_cast<int>(r));
+  return 0;
+}
+
+extern long long g_launches;
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid, cudaStream_t st) {
+  auto kfn = gemm_kernel<BN, EPI, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  kfn<<<grid, GEMM_THREADS, TileCfg<BN>::kSmemBytes, st>>>(ta, tb, d);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}
+
+template <int BN, int EPI>
+static int dispatch_major(const mh_gemm_args* a, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d,
+                          int grid, cudaStream_t st) {
+  if (!a->a_mn && !a->b_mn) return launch<BN, EPI, false, false>(ta, tb, d, grid, st);
+  if (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
+    if (a->a_mn && a->b_mn) return launch<BN, EPI == MH_EPI_F32 ? MH_EPI_F32 : MH_EPI_BF16, true, true>(ta, tb, d, grid, st);
+    if (a->a_mn && !a->b_mn) return launch<BN, EPI == MH_EPI_F32 ? MH_EPI_F32 : MH_EPI_BF16, true, false>(ta, tb, d, grid, st);
+    return launch<BN, EPI == MH_EPI_F32 ? MH_EPI_F32 : MH_EPI_BF16, false, true>(ta, tb, d, grid, st);
+  }
+  set_error("MN-major operands are only built for MH_EPI_BF16 / MH_EPI_F32");
+  return 1;
+}
+
+template <int BN>
+static int dispatch_epi(const mh_gemm_args* a, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid,
+                        cudaStream_t st) {
+  switch (a->epilogue) {
+    case MH_EPI_BF16: return dispatch_major<BN, MH_EPI_BF16>(a, ta, tb, d, grid, st);
+    case MH_EPI_GELU: return dispatch_major<BN, MH_EPI_GELU>(a, ta, tb, d, grid, st);
+    case MH_EPI_RES: return dispatch_major<BN, MH_EPI_RES>(a, ta, tb, d, grid, st);
+    case MH_EPI_F32: return dispatch_major<BN, MH_EPI_F32>(a, ta, tb, d, grid, st);
+    case MH_EPI_DGELU: return dispatch_major<BN, MH_EPI_DGELU>(a, ta, tb, d, grid, st);
+    case MH_EPI_ADD: return dispatch_major<BN, MH_EPI_ADD>(a, ta, tb, d, grid, st);
+  }
+  set_error("unknown epilogue %d", a->epilogue);
+  return 1;
+}
+
+}  // namespace mh
+
+extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
+  using namespace mh;
+  MH_CHECK(a != nullptr, "null args");
+  MH_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "bad GEMM shape %d x %d x %d", a->M, a->N, a->K);
+  MH_CHECK(a->N % 8 == 0, "N must be a multiple of 8 (got %d)", a->N);
+  MH_CHECK(a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, "D must be 16-byte aligned, ldd %% 8 == 0");
+  if (a->epilogue == MH_EPI_RES || a->epilogue == MH_EPI_DGELU || a->epilogue == MH_EPI_ADD)
+    MH_CHECK(a->aux_in != nullptr && a->ld_aux % 8 == 0, "epilogue %d needs aux_in", a->epilogue);
+  if (a->epilogue == MH_EPI_GELU && a->aux_out != nullptr) MH_CHECK(a->ld_aux % 8 == 0, "ld_aux %% 8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  const int sms = sm_count();
+  const int num_m = (a->M + BM - 1) / BM;
+  int bn = a->block_n;
+  if (bn == 0) bn = (a->N >= 256 && num_m * ((a->N + 255) / 256) >= sms) ? 256 : 128;
+  MH_CHECK(bn == 128 || bn == 256, "block_n must be 128 or 256");
+  const int num_n = (a->N + bn - 1) / bn;
+  const int kblocks = (a->K + BK - 1) / BK;
+  int splits = 1;
+  if (a->epilogue == MH_EPI_F32) {
+    splits = a->split_k;
+    if (splits <= 0) {
+      splits = sms / (num_m * num_n);
+      if (splits < 1) splits = 1;
+      if (splits > kblocks / 4) splits = kblocks / 4 > 0 ? kblocks / 4 : 1;  // keep >= 4 k-blocks per split
+      if (splits > 32) splits = 32;
+    }
+    if (splits > kblocks) splits = kblocks;
+    // avoid empty trailing splits
+    const int per = (kblocks + splits - 1) / splits;
+    splits = (kblocks + per - 1) / per;
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a->a_mn) rc = make_tmap_2d(&ta, a->A, a->M, a->K, a->lda, BK, BM);
+  else rc = make_tmap_2d(&ta, a->A, a->K, a->M, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap_2d(&tb, a->B, a->N, a->K, a->ldb, BK, bn);
+  else rc = make_tmap_2d(&tb, a->B, a->K, a->N, a->ldb, 64, BK);
+  if (rc) return rc;
+
+  GemmDev d;
+  d.M = a->M; d.N = a->N; d.K = a->K;
+  d.D = a->D; d.ldd = a->ldd;
+  d.bias = a->bias;
+  d.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
+  d.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
+  d.ld_aux = a->ld_aux;
+  d.mask = a->mask;
+  d.drop = make_drop(a->p_drop, a->seed, a->site);
+  d.split_k = splits;
+  const int tiles = num_m * num_n * splits;
+  const int grid = tiles < sms ? tiles : sms;
+  if (bn == 256) return dispatch_epi<256>(a, ta, tb, d, grid, st);
+  return dispatch_epi<128>(a, ta, tb, d, grid, st);
+}

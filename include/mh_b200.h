@@ -64,15 +64,15 @@ int mh_gemm(const mh_gemm_args* args, void* stream);
  * and the reshapes at :199-201, :231.
  *   qkv : bf16 [B*T, 3*E] rows = frames, columns = [q | k | v], E = 64 * heads
  *   kv_len[b] : number of valid (non padded) keys of batch element b (suffix padding)
- *   out : bf16 [B*T, E]      lse : f32 [B, heads, T] (log-sum-exp of the scaled scores)
+ *   out : bf16 [B*T, E]      lse : f32 [B, heads, T] (base-2 log-sum-exp of the scaled scores)
  *   dropout on the probabilities regenerated from (seed, site) in the backward.
  * ------------------------------------------------------------------------------------- */
 int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, int B, int T, int heads,
                 int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
-/* dqkv : bf16 [B*T, 3*E];  delta : f32 scratch [B, heads, T] */
+/* dqkv : bf16 [B*T, 3*E];  delta : f32 scratch [B, heads, T];  dq_acc : f32 scratch [B*T, E] */
 int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
-                float* delta, void* dqkv, int B, int T, int heads, int causal, float p_drop, uint64_t seed,
-                uint32_t site, void* stream);
+                float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal, float p_drop,
+                uint64_t seed, uint32_t site, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNorm family (module.py:121-123,129-131,232-236: dropout -> +residual -> LayerNorm is
@@ -82,10 +82,15 @@ int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void*
  * ------------------------------------------------------------------------------------- */
 int mh_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                      int rows, int cols, float eps, float p_drop, uint64_t seed, uint32_t site, void* stream);
-/* dx (bf16) = LN backward of dy (+ dres if given);  dgamma/dbeta (f32 [cols]) are accumulated. */
+/* dy_eff = dy * keep-mask(p_in, seed_in, site_in)  (the dropout that was applied to the LN
+ * output in the forward, if any);  dx (bf16) = LN backward of dy_eff;  dx_drop (optional)
+ * = dx * keep-mask(p_out, ...) -- the gradient w.r.t. the GEMM output that fed this LN through
+ * dropout + residual, ready to be the A operand of the dgrad / wgrad GEMMs.
+ * dgamma / dbeta (f32 [cols]) are accumulated (atomicAdd). */
 int mh_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, float p_drop,
-                     uint64_t seed, uint32_t site, void* stream);
+                     void* dx, void* dx_drop, float* dgamma, float* dbeta, int rows, int cols, float p_in,
+                     uint64_t seed_in, uint32_t site_in, float p_out, uint64_t seed_out, uint32_t site_out,
+                     void* stream);
 
 /* column sums: out[n] += sum_m x[m, n]  (bias gradients).  x bf16 [rows, ld] */
 int mh_colsum(const void* x, long long ld, float* out, int rows, int cols, void* stream);
@@ -139,6 +144,8 @@ int mh_ce_fwd(const void* logits, const long long* labels, const int* n_valid, f
               int n_rows, int n_class, void* stream);
 int mh_ce_bwd(const void* logits, const long long* labels, const int* n_valid, const float* grad_scale,
               void* dlogits, int n_rows, int n_class, void* stream);
+/* loss[0] = weight * acc[0] / acc[1];  grad_scale[0] = weight / acc[1]  (device side) */
+int mh_ce_finalize(const float* acc, float weight, float* loss, float* grad_scale, void* stream);
 /* KD (distillation/pretrain_expert.py:83-92): hard = CE(student), soft = KL(softmax(t/T) ||
  * softmax(s/T)) summed over rows; acc[0] += sum CE_s, acc[1] += count, acc[2] += sum KL,
  * acc[3] += sum CE_t, acc[4] += rows.  Backward: dlogits = w_hard[0]*(p_s - onehot) +
@@ -147,6 +154,9 @@ int mh_kd_fwd(const void* s_logits, const void* t_logits, const long long* label
               float* acc, int n_rows, int n_class, void* stream);
 int mh_kd_bwd(const void* s_logits, const void* t_logits, const long long* labels, const int* n_valid, float T,
               const float* w_hard, const float* w_soft, void* dlogits, int n_rows, int n_class, void* stream);
+/* out[0] = total, out[1] = hard CE, out[2] = soft KL(batchmean), out[3] = teacher CE;
+ * w_hard[0] = (1-alpha)/count, w_soft[0] = alpha/rows */
+int mh_kd_finalize(const float* acc, float alpha, float* out, float* w_hard, float* w_soft, void* stream);
 /* L1 + cosine per-frame criterion (north_star; DistilHuBERT form):
  *   acc[0] += sum |p - t|, acc[1] += sum -logsigmoid(cos(p, t));  rows of `cols` bf16.
  *   backward: dpred = w_l1[0]*sign(p - t) + w_cos[0]*d(-logsigmoid(cos))/dp */

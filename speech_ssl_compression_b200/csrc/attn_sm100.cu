@@ -1,0 +1,571 @@
+// Fused multi-head attention for sm_100a (head_dim = 64), flash style: the T x T score
+// matrix lives only in TMEM / shared memory.
+//
+// Forward, one CTA per (batch, head, 128-query block), 2 CTAs resident per SM:
+//   warp 4 : TMA producer   -- Q once, then K_j / V_j tiles (128 keys) into a 2-stage ring
+//   warp 5 : MMA issuer     -- S = Q K_j^T (tcgen05, fp32 in TMEM), then O_j = P_j V_j
+//   warps 0-3 : softmax     -- thread t owns query row t: tcgen05.ld of its S row, scale,
+//               key-padding / causal mask, running max / sum (no shuffles needed), Philox
+//               dropout, bf16 P written to smem in the 128B-swizzled K-major layout the next
+//               MMA reads as its A operand; O accumulated in registers with the usual
+//               exp2(m_old - m_new) correction.
+// V is consumed straight from the QKV GEMM output as an MN-major B operand (no transpose).
+//
+// Backward, one CTA per (batch, head, 128-key block) looping over query blocks:
+//   S = Q K^T and dP = dO V^T into TMEM; 8 warps rebuild P = exp2(S*c - lse), apply the
+//   regenerated dropout mask, form dS = P * (dP - delta) and write P_drop / dS (bf16) to smem;
+//   dV += P_drop^T dO, dK += dS^T Q (MN-major A and B operands, accumulating in TMEM across
+//   the whole query loop) and dQ_i = dS K (red.global.add.f32 into an fp32 workspace).
+#include "mh_b200.h"
+#include "mh_common.cuh"
+#include "mh_ptx.cuh"
+
+namespace mh {
+extern long long g_launches;
+int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
+                 long long stride2, int box0, int box1);
+
+constexpr int HD = 64;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnParams {
+  const int* kv_len;
+  __nv_bfloat16* out;   // [B*T, E]
+  float* lse;           // [B, H, T] base-2 log-sum-exp of the scaled scores
+  int B, T, H, E;
+  int causal;
+  float scale_log2;     // (1/sqrt(64)) * log2(e)
+  DropCfg drop;
+};
+
+// byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
+__device__ __forceinline__ uint32_t swz(int r, int ch) { return r * 128 + ((ch ^ (r & 7)) << 4); }
+
+constexpr int FWD_SMEM = TILE_BYTES * (1 + 2 + 2 + 2) + 128;  // 2 CTAs / SM: <= 115,712 B each
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs a 1024-byte aligned base
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
+  uint8_t* sP = sV + 2 * TILE_BYTES;   // 2 swizzle atoms (keys 0-63 | 64-127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * BQ;
+  const int kv_len = min(p.kv_len ? p.kv_len[b] : p.T, p.T);
+  int kv_end = kv_len;
+  if (p.causal) kv_end = min(kv_end, q0 + BQ);
+  const int n_kv = (kv_end + BKV - 1) / BKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;        // 128 columns
+  const uint32_t tmem_o = tmem_base + 128;  // 64 columns
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tm, q_full, h * HD, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        tma_load_3d(sK + st * TILE_BYTES, &tm, &kv_full[st], p.E + h * HD, j * BKV, b);
+        tma_load_3d(sV + st * TILE_BYTES, &tm, &kv_full[st], 2 * p.E + h * HD, j * BKV, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, false, false);
+      const uint32_t idesc_o = make_idesc_bf16(BQ, HD, false, true);
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(sQ), bk = smem_u32(sK + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_s, make_sdesc(a + k * 32, 0, 1024), make_sdesc(bk + k * 32, 0, 1024), idesc_s, k > 0);
+        umma_commit(s_full);
+      };
+      if (n_kv > 0) issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);  // P_j in smem, S_j / O_{j-1} consumed
+        tc_fence_after();
+        const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_bf16(tmem_o, make_sdesc(ap + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
+                    make_sdesc(bv + k * 2048, TILE_BYTES, 1024), idesc_o, k > 0);
+        umma_commit(&kv_empty[st]);
+        umma_commit(o_full);
+        if (j + 1 < n_kv) issue_s(j + 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int r = threadIdx.x;  // query row inside the tile == TMEM lane
+    const int q = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint64_t row_id = (static_cast<uint64_t>(b) * p.H + h) * p.T + q;
+    const uint64_t groups_per_row = (p.T + 7) >> 3;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int k0 = j * BKV;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      int lim = kv_len - k0;                       // keys [0, lim) of this block are visible
+      if (p.causal) lim = min(lim, q - k0 + 1);
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_s + lane_off + c * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < lim) mx = fmaxf(mx, __uint_as_float(rr[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_use = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_use);  // m_run = -inf -> 0
+      // pass 2: probabilities, row sum, dropout, bf16 P into swizzled smem
+      float l_blk = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_s + lane_off + c * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int kk = c * 32 + g * 8 + i;
+            const float e = exp2f(__uint_as_float(rr[g * 8 + i]) * p.scale_log2 - m_use);
+            pv[i] = kk < lim ? e : 0.f;
+            l_blk += pv[i];
+          }
+          if (p.drop.thresh != 0) {
+            const uint32_t keep = drop_keep8(p.drop, row_id * groups_per_row + ((k0 + c * 32 + g * 8) >> 3));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = ((keep >> i) & 1) ? pv[i] * p.drop.scale : 0.f;
+          }
+          const int kc = c * 32 + g * 8;  // key column inside the block
+          uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
+          *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
+        }
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // O += P V
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_o + lane_off + c * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(rr[i]);
+      }
+      tc_fence_before();
+    }
+    if (q < p.T) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + q) * p.E + h * HD;
+#pragma unroll
+      for (int g = 0; g < HD / 8; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = o[g * 8 + i] * inv;
+        stg128(dst + g * 8, f32_to_bf16x8(v));
+      }
+      p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+// ----------------------------------------------------------------------------- backward
+// delta[b,h,q] = sum_d dO[row, h*64+d] * O[row, h*64+d]; one warp per (row, head).
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                  int B, int T, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);  // (row, head) pair
+  const long long total = static_cast<long long>(B) * T * H;
+  if (w >= total) return;
+  const long long row = w / H;
+  const int h = static_cast<int>(w % H);
+  const long long off = row * (static_cast<long long>(H) * HD) + h * HD + lane * 2;
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + off);
+  const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(d_o + off);
+  float s = __bfloat162float(a.x) * __bfloat162float(g.x) + __bfloat162float(a.y) * __bfloat162float(g.y);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const long long bb = row / T, t = row % T;
+    delta[(bb * H + h) * T + t] = s;
+  }
+}
+
+struct AttnBwdParams {
+  const int* kv_len;
+  const float* lse;     // base-2
+  const float* delta;
+  float* dq_acc;        // fp32 [B*T, E], zero-initialised
+  __nv_bfloat16* dqkv;  // [B*T, 3E]
+  int B, T, H, E;
+  int causal;
+  float scale, scale_log2;
+  DropCfg drop;
+};
+
+// smem: K, V (16 KB each) | Q[2], dO[2] (64 KB) | P (32 KB) | dS (32 KB)
+constexpr int BWD_SMEM = TILE_BYTES * (2 + 4 + 2 + 2) + 1024 + 256;
+constexpr int BWD_THREADS = 320;  // warps 0-7 compute, 8 = TMA, 9 = MMA
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sQ = sV + TILE_BYTES;        // 2 stages
+  uint8_t* sdO = sQ + 2 * TILE_BYTES;   // 2 stages
+  uint8_t* sP = sdO + 2 * TILE_BYTES;   // [128 q rows][128 keys] as 2 atoms of 64 keys
+  uint8_t* sdS = sP + 2 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * TILE_BYTES);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;  // S and dP ready in TMEM
+  uint64_t* pds_full = bars + 6;  // P / dS written to smem (256 arrivals)
+  uint64_t* dq_full = bars + 7;   // dQ_i ready in TMEM (and all MMAs reading P / dS retired)
+  uint64_t* fin_full = bars + 8;  // dK / dV final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kb * BKV;
+  const int kv_len = min(p.kv_len ? p.kv_len[b] : p.T, p.T);
+  const int n_q = (p.T + BQ - 1) / BQ;
+  const int i_begin = p.causal ? k0 / BQ : 0;  // query blocks that can see this key block
+  const bool active = k0 < kv_len;             // a fully padded key block has zero gradient
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(fin_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
+                 tm_dq = tmem_base + 384;
+
+  if (active) {
+    if (warp == 8) {
+      if (elect_one()) {
+        mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+        tma_load_3d(sK, &tm_qkv, kv_full, p.E + h * HD, k0, b);
+        tma_load_3d(sV, &tm_qkv, kv_full, 2 * p.E + h * HD, k0, b);
+        for (int i = i_begin, n = 0; i < n_q; ++i, ++n) {
+          const int st = n & 1;
+          mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[st], 2 * TILE_BYTES);
+          tma_load_3d(sQ + st * TILE_BYTES, &tm_qkv, &q_full[st], h * HD, i * BQ, b);
+          tma_load_3d(sdO + st * TILE_BYTES, &tm_do, &q_full[st], h * HD, i * BQ, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 9) {
+      if (elect_one()) {
+        const uint32_t id_s = make_idesc_bf16(BQ, BKV, false, false);   // S, dP: [q x k], both K-major
+        const uint32_t id_kv = make_idesc_bf16(BKV, HD, true, true);    // dV, dK: [k x hd], A and B MN-major
+        const uint32_t id_q = make_idesc_bf16(BQ, HD, false, true);     // dQ: [q x hd], A K-major, B MN-major
+        mbar_wait(kv_full, 0);
+        const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
+        auto issue_sdp = [&](int n) {
+          const int st = n & 1;
+          mbar_wait(&q_full[st], (n >> 1) & 1);
+          tc_fence_after();
+          const uint32_t aq = smem_u32(sQ + st * TILE_BYTES), ado = smem_u32(sdO + st * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tm_s, make_sdesc(aq + k * 32, 0, 1024), make_sdesc(ak + k * 32, 0, 1024), id_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tm_dp, make_sdesc(ado + k * 32, 0, 1024), make_sdesc(av + k * 32, 0, 1024), id_s, k > 0);
+          umma_commit(sdp_full);
+        };
+        const int n_iter = n_q - i_begin;
+        if (n_iter > 0) issue_sdp(0);
+        for (int n = 0; n < n_iter; ++n) {
+          const int st = n & 1;
+          mbar_wait(pds_full, n & 1);
+          tc_fence_after();
+          const uint32_t aq = smem_u32(sQ + st * TILE_BYTES), ado = smem_u32(sdO + st * TILE_BYTES);
+          // contraction over the 128 query rows: 8 steps of 16 rows (2048 B per step in every tile)
+#pragma unroll
+          for (int k = 0; k < BQ / 16; ++k) {
+            umma_bf16(tm_dv, make_sdesc(ap + k * 2048, TILE_BYTES, 1024), make_sdesc(ado + k * 2048, TILE_BYTES, 1024),
+                      id_kv, (n > 0 || k > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < BQ / 16; ++k) {
+            umma_bf16(tm_dk, make_sdesc(ads + k * 2048, TILE_BYTES, 1024), make_sdesc(aq + k * 2048, TILE_BYTES, 1024),
+                      id_kv, (n > 0 || k > 0) ? 1u : 0u);
+          }
+          // dQ_i = dS K : contraction over the 128 keys
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            umma_bf16(tm_dq, make_sdesc(ads + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
+                      make_sdesc(ak + k * 2048, TILE_BYTES, 1024), id_q, k > 0);
+          }
+          umma_commit(&q_empty[st]);
+          umma_commit(dq_full);
+          if (n + 1 < n_iter) issue_sdp(n + 1);
+        }
+        umma_commit(fin_full);
+      }
+      __syncwarp();
+    } else {
+      // ---------------------------------------------------------------- compute warps
+      const int quad = warp & 3, half = warp >> 2;
+      const int r = quad * 32 + lane;  // query row inside the tile (S / dP / dQ) or key row (dK / dV)
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      const uint64_t groups_per_row = (p.T + 7) >> 3;
+      const int n_iter = n_q - i_begin;
+      for (int n = 0; n < n_iter; ++n) {
+        const int i = i_begin + n;
+        const int q = i * BQ + r;
+        const bool q_ok = q < p.T;
+        const long long sidx = (static_cast<long long>(b) * p.H + h) * p.T + q;
+        const float lse = q_ok ? p.lse[sidx] : INFINITY;
+        const float dl = q_ok ? p.delta[sidx] : 0.f;
+        const uint64_t row_id = static_cast<uint64_t>(sidx);
+        int lim = kv_len - k0;
+        if (p.causal) lim = min(lim, q - k0 + 1);
+        mbar_wait(sdp_full, n & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {  // this warp's 64 key columns in two chunks of 32
+          const int kc0 = half * 64 + c * 32;
+          uint32_t rs[32], rd[32];
+          tmem_ld32(tm_s + lane_off + kc0, rs);
+          tmem_ld32(tm_dp + lane_off + kc0, rd);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pd[8], ds[8];
+            uint32_t keep = 0xFFu;
+            if (p.drop.thresh != 0) keep = drop_keep8(p.drop, row_id * groups_per_row + ((k0 + kc0 + g * 8) >> 3));
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int kk = kc0 + g * 8 + t;
+              float pr = exp2f(__uint_as_float(rs[g * 8 + t]) * p.scale_log2 - lse);
+              pr = (kk < lim && q_ok) ? pr : 0.f;
+              const float z = ((keep >> t) & 1) ? p.drop.scale : 0.f;
+              pd[t] = pr * z;
+              ds[t] = pr * (__uint_as_float(rd[g * 8 + t]) * z - dl) * p.scale;
+            }
+            const int kc = kc0 + g * 8;
+            const uint32_t off = (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
+            *reinterpret_cast<uint4*>(sP + off) = f32_to_bf16x8(pd);
+            *reinterpret_cast<uint4*>(sdS + off) = f32_to_bf16x8(ds);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(pds_full);
+        // dQ_i: this warp's 32 of the 64 head-dim columns
+        mbar_wait(dq_full, n & 1);
+        tc_fence_after();
+        {
+          uint32_t rq[32];
+          tmem_ld32(tm_dq + lane_off + half * 32, rq);
+          tmem_ld_wait();
+          if (q_ok) {
+            float* dst = p.dq_acc + (static_cast<long long>(b) * p.T + q) * p.E + h * HD + half * 32;
+#pragma unroll
+            for (int t = 0; t < 32; t += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + t), "f"(__uint_as_float(rq[t])),
+                           "f"(__uint_as_float(rq[t + 1])), "f"(__uint_as_float(rq[t + 2])),
+                           "f"(__uint_as_float(rq[t + 3]))
+                           : "memory");
+          }
+        }
+        tc_fence_before();
+      }
+      // final dK / dV: row r = key k0 + r
+      mbar_wait(fin_full, 0);
+      tc_fence_after();
+      const int key = k0 + r;
+      uint32_t rk[32], rv[32];
+      tmem_ld32(tm_dk + lane_off + half * 32, rk);
+      tmem_ld32(tm_dv + lane_off + half * 32, rv);
+      tmem_ld_wait();
+      if (key < p.T) {
+        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + half * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float a[8], c[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            a[t] = n_iter > 0 ? __uint_as_float(rk[g * 8 + t]) : 0.f;
+            c[t] = n_iter > 0 ? __uint_as_float(rv[g * 8 + t]) : 0.f;
+          }
+          stg128(base + p.E + g * 8, f32_to_bf16x8(a));
+          stg128(base + 2 * p.E + g * 8, f32_to_bf16x8(c));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // fully padded key block: dK = dV = 0
+    const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int key = k0 + r;
+    if (key < p.T) {
+      __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + half * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        stg128(base + p.E + g * 8, make_uint4(0, 0, 0, 0));
+        stg128(base + 2 * p.E + g * 8, make_uint4(0, 0, 0, 0));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// dqkv[:, 0:E] = bf16(dq_acc)
+__global__ void dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, long long rows, int E) {
+  const int cpr = E >> 3;
+  const long long total = rows * cpr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cpr;
+    const int c = static_cast<int>(i % cpr) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(dq + r * E + c);
+    const float4 bb = *reinterpret_cast<const float4*>(dq + r * E + c + 4);
+    stg128(dqkv + r * 3 * E + c,
+           make_uint4(f32x2_to_bf16(a.x, a.y), f32x2_to_bf16(a.z, a.w), f32x2_to_bf16(bb.x, bb.y), f32x2_to_bf16(bb.z, bb.w)));
+  }
+}
+}  // namespace mh
+
+using namespace mh;
+
+extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, int B, int T, int heads, int causal,
+                           float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_fwd: bad shape B=%d T=%d heads=%d", B, T, heads);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int E = heads * HD;
+  CUtensorMap tm;
+  int rc = make_tmap_3d(&tm, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, BQ);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    configured = true;
+  }
+  AttnParams p;
+  p.kv_len = kv_len; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.lse = lse;
+  p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
+  p.scale_log2 = 0.125f * LOG2E;
+  p.drop = make_drop(p_drop, seed, site);
+  attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, p);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}
+
+extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                           float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal, float p_drop,
+                           uint64_t seed, uint32_t site, void* stream) {
+  MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_bwd: bad shape B=%d T=%d heads=%d", B, T, heads);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int E = heads * HD;
+  const long long rows = static_cast<long long>(B) * T;
+  CUtensorMap tq, tdo;
+  int rc = make_tmap_3d(&tq, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, BQ);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tdo, dout, E, T, B, E, static_cast<long long>(T) * E, HD, BQ);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    configured = true;
+  }
+  const long long pairs = rows * heads;
+  attn_delta_kernel<<<static_cast<int>((pairs + 7) / 8), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T, heads);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  MH_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * E, st));
+  AttnBwdParams p;
+  p.kv_len = kv_len; p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
+  p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
+  p.drop = make_drop(p_drop, seed, site);
+  attn_bwd_kernel<<<dim3((T + BKV - 1) / BKV, heads, B), BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, p);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  long long g = (rows * (E / 8) + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (g > cap) g = cap;
+  dq_finish_kernel<<<static_cast<int>(g), 256, 0, st>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), rows, E);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}

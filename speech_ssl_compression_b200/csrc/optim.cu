@@ -1,0 +1,102 @@
+// Fused optimizer step over flat fp32 buffers (runner.py:411-427: grad /= n, global-norm clip,
+// Adam, zero_grad) -- one HBM pass: reads p, g, m, v; writes p, m, v (and zeros g).
+#include "mh_b200.h"
+#include "mh_common.cuh"
+
+namespace mh {
+extern long long g_launches;
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (; i + 4 <= n; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + i));
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (i < n && i + 4 > n)
+    for (long long j = i; j < n; ++j) s += x[j] * x[j];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+    t += __shfl_xor_sync(0xffu, t, 4);
+    t += __shfl_xor_sync(0xffu, t, 2);
+    t += __shfl_xor_sync(0xffu, t, 1);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            float lr, float b1, float b2, float eps, float wd, const int* __restrict__ step_ptr, float grad_scale,
+            float max_norm, const float* __restrict__ sumsq, int zero_grad) {
+  const int step = *step_ptr;
+  float clip = 1.f;
+  bool skip = false;
+  if (sumsq != nullptr) {
+    const float norm = sqrtf(*sumsq) * grad_scale;
+    if (!(norm == norm) || isinf(norm)) skip = true;  // runner.py:417-425: NaN grad norm skips the step
+    if (max_norm > 0.f) clip = fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const float gs = grad_scale * clip;
+  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (; i < n; i += stride) {  // n is padded to a multiple of 4 by the host
+    float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<float4*>(g + i);
+    float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    if (!skip) {
+      float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float gj = gp[j] * gs;
+        if (wd != 0.f) gj += wd * pp[j];
+        mp[j] = b1 * mp[j] + (1.f - b1) * gj;
+        vp[j] = b2 * vp[j] + (1.f - b2) * gj * gj;
+        const float denom = sqrtf(vp[j]) * inv_sqrt_bc2 + eps;
+        pp[j] -= step_size * mp[j] / denom;
+      }
+      *reinterpret_cast<float4*>(p + i) = pv;
+      *reinterpret_cast<float4*>(m + i) = mv;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    }
+    if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+}  // namespace mh
+
+using namespace mh;
+#define ST reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int mh_sumsq(const float* x, long long n, float* out, void* stream) {
+  if (n == 0) return 0;
+  long long g = (n / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  sumsq_kernel<<<static_cast<int>(g), 256, 0, ST>>>(x, n, out);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}
+
+extern "C" int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, const int* step, float grad_scale,
+                            float max_norm, const float* sumsq, int zero_grad, void* stream) {
+  MH_CHECK(n % 4 == 0, "adam: flat buffer length must be a multiple of 4 (got %lld)", n);
+  if (n == 0) return 0;
+  long long g = (n / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (g > cap) g = cap;
+  adam_kernel<<<static_cast<int>(g), 256, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                   step, grad_scale, max_norm, sumsq, zero_grad);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}

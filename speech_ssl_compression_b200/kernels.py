@@ -73,3 +73,222 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None, aux
     args.block_n, args.split_k = block_n, split_k
     L.check(L.lib().mh_gemm(byref(args), _s()), "mh_gemm")
     return out
+
+
+def _f(x):
+    return c_float(float(x))
+
+
+def _call(name, *args):
+    L.check(getattr(L.lib(), name)(*args), name)
+
+
+# ------------------------------------------------------------------------------ attention
+def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0):
+    """qkv: bf16 [B*T, 3*64*heads]; kv_len: int32 [B] (or None).  Returns (out [B*T, E], lse [B,H,T])."""
+    E = 64 * heads
+    if qkv.dtype != bf16 or tuple(qkv.shape) != (B * T, 3 * E) or not qkv.is_contiguous():
+        raise ValueError(f"attn_fwd: qkv must be contiguous bf16 [{B * T}, {3 * E}], got {tuple(qkv.shape)}")
+    out = torch.empty(B * T, E, device=qkv.device, dtype=bf16)
+    lse = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
+    _call("mh_attn_fwd", _p(qkv), _p(kv_len), _p(out), _p(lse), c_int(B), c_int(T), c_int(heads), c_int(int(causal)),
+          _f(p_drop), c_uint64(seed), c_uint32(site), _s())
+    return out, lse
+
+
+def attn_bwd(qkv, kv_len, out, dout, lse, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0):
+    E = 64 * heads
+    if dout.dtype != bf16 or not dout.is_contiguous() or tuple(dout.shape) != (B * T, E):
+        raise ValueError("attn_bwd: dout must be contiguous bf16 [B*T, E]")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
+    dq_acc = torch.empty(B * T, E, device=qkv.device, dtype=torch.float32)
+    _call("mh_attn_bwd", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(delta), _p(dq_acc), _p(dqkv), c_int(B),
+          c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), _s())
+    return dqkv
+
+
+# ------------------------------------------------------------------------------ layer norm
+def layernorm_fwd(x, gamma, beta, eps=1e-5, *, p_drop=0.0, seed=0, site=0):
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _call("mh_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), c_int(rows), c_int(cols), _f(eps),
+          _f(p_drop), c_uint64(seed), c_uint32(site), _s())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, want_drop=False, p_in=0.0, seed_in=0, site_in=0,
+                  p_out=0.0, seed_out=0, site_out=0):
+    """Returns (dx, dx_drop or None).  dgamma / dbeta (fp32 [cols]) are accumulated in place."""
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    dx_drop = torch.empty_like(x) if want_drop else None
+    _call("mh_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dx_drop), _p(dgamma), _p(dbeta),
+          c_int(rows), c_int(cols), _f(p_in), c_uint64(seed_in), c_uint32(site_in), _f(p_out), c_uint64(seed_out),
+          c_uint32(site_out), _s())
+    return dx, dx_drop
+
+
+def colsum_add(x, out):
+    """out[n] += sum_m x[m, n]  (x bf16 [rows, cols], out fp32 [cols])"""
+    _call("mh_colsum", _p(x), c_longlong(x.stride(0)), _p(out), c_int(x.shape[0]), c_int(x.shape[1]), _s())
+
+
+# ------------------------------------------------------------------------------ prep / movement
+def weight_prep(src, mask, dst, dst_t=None):
+    """src fp32 [rows, cols] (contiguous), mask bool/u8 or None; dst bf16 view [rows, cols] (any ld);
+    dst_t bf16 view [cols, rows] or None."""
+    rows, cols = src.shape
+    _call("mh_weight_prep", _p(src), _p(mask), _p(dst), c_longlong(dst.stride(0)), _p(dst_t),
+          c_longlong(dst_t.stride(0) if dst_t is not None else 0), c_int(rows), c_int(cols), _s())
+
+
+def bias_prep(src, mask, dst):
+    _call("mh_bias_prep", _p(src), _p(mask), _p(dst), c_int(src.numel()), _s())
+
+
+def to_bf16(src, dst=None):
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=bf16)
+    _call("mh_cast_f32_to_bf16", _p(src), _p(dst), c_longlong(src.numel()), _s())
+    return dst
+
+
+def to_f32(src, dst=None):
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    _call("mh_cast_bf16_to_f32", _p(src), _p(dst), c_longlong(src.numel()), _s())
+    return dst
+
+
+def mask_rows_to_bf16(src, zero_row, dst=None):
+    rows, cols = src.shape
+    if dst is None:
+        dst = torch.empty(rows, cols, device=src.device, dtype=bf16)
+    _call("mh_mask_rows_f32_to_bf16", _p(src), _p(zero_row), _p(dst), c_int(rows), c_int(cols), _s())
+    return dst
+
+
+def zero_rows_(x, zero_row):
+    _call("mh_zero_rows_bf16", _p(x), _p(zero_row), c_int(x.shape[0]), c_int(x.shape[1]), _s())
+    return x
+
+
+def select_rows(sel, idx=None, count=None):
+    rows = sel.numel()
+    if idx is None:
+        idx = torch.empty(rows, device=sel.device, dtype=torch.int32)
+    if count is None:
+        count = torch.empty(1, device=sel.device, dtype=torch.int32)
+    _call("mh_select_rows", _p(sel), _p(idx), _p(count), c_int(rows), _s())
+    return idx, count
+
+
+def gather_rows(src, idx, n_idx, dst=None):
+    cols = src.shape[1]
+    if dst is None:
+        dst = torch.empty(n_idx, cols, device=src.device, dtype=bf16)
+    _call("mh_gather_rows", _p(src), _p(idx), _p(dst), c_int(n_idx), c_int(cols), _s())
+    return dst
+
+
+def scatter_rows_add_(src, idx, n_idx, dst):
+    _call("mh_scatter_rows_add", _p(src), _p(idx), _p(dst), c_int(n_idx), c_int(src.shape[1]), _s())
+    return dst
+
+
+def gather_labels(label, idx, n_idx):
+    dst = torch.empty(n_idx, device=label.device, dtype=torch.int64)
+    _call("mh_gather_labels", _p(label), _p(idx), _p(dst), c_int(n_idx), _s())
+    return dst
+
+
+# ------------------------------------------------------------------------------ criteria
+def ce_fwd(logits, labels, acc, n_valid=None, row_loss=None):
+    _call("mh_ce_fwd", _p(logits), _p(labels), _p(n_valid), _p(row_loss), _p(acc), c_int(logits.shape[0]),
+          c_int(logits.shape[1]), _s())
+
+
+def ce_bwd(logits, labels, grad_scale, n_valid=None):
+    d = torch.empty_like(logits)
+    _call("mh_ce_bwd", _p(logits), _p(labels), _p(n_valid), _p(grad_scale), _p(d), c_int(logits.shape[0]),
+          c_int(logits.shape[1]), _s())
+    return d
+
+
+def ce_finalize(acc, weight, loss, grad_scale):
+    _call("mh_ce_finalize", _p(acc), _f(weight), _p(loss), _p(grad_scale), _s())
+
+
+def kd_fwd(s_logits, t_logits, labels, T, acc, n_valid=None):
+    _call("mh_kd_fwd", _p(s_logits), _p(t_logits), _p(labels), _p(n_valid), _f(T), _p(acc), c_int(s_logits.shape[0]),
+          c_int(s_logits.shape[1]), _s())
+
+
+def kd_bwd(s_logits, t_logits, labels, T, w_hard, w_soft, n_valid=None):
+    d = torch.empty_like(s_logits)
+    _call("mh_kd_bwd", _p(s_logits), _p(t_logits), _p(labels), _p(n_valid), _f(T), _p(w_hard), _p(w_soft), _p(d),
+          c_int(s_logits.shape[0]), c_int(s_logits.shape[1]), _s())
+    return d
+
+
+def kd_finalize(acc, alpha, out, w_hard, w_soft):
+    _call("mh_kd_finalize", _p(acc), _f(alpha), _p(out), _p(w_hard), _p(w_soft), _s())
+
+
+def l1cos_fwd(pred, target, acc):
+    _call("mh_l1cos_fwd", _p(pred), _p(target), _p(acc), c_int(pred.shape[0]), c_int(pred.shape[1]), _s())
+
+
+def l1cos_bwd(pred, target, w_l1, w_cos):
+    d = torch.empty_like(pred)
+    _call("mh_l1cos_bwd", _p(pred), _p(target), _p(w_l1), _p(w_cos), _p(d), c_int(pred.shape[0]), c_int(pred.shape[1]), _s())
+    return d
+
+
+# ------------------------------------------------------------------------------ pruning objects
+def abs_kth_smallest(tensors, k):
+    """Exact k-th smallest |w| (1-based) over the concatenation of fp32 tensors.
+    Returns a device uint64[3]: (threshold bit pattern, #strictly below, #equal)."""
+    dev = tensors[0].device
+    n = len(tensors)
+    ptrs = (c_void_p * n)(*[t.data_ptr() for t in tensors])
+    sizes = (c_longlong * n)(*[t.numel() for t in tensors])
+    ws = torch.zeros(2048 + 8, device=dev, dtype=torch.int64)
+    res = torch.zeros(3, device=dev, dtype=torch.int64)
+    _call("mh_abs_kth_smallest", ptrs, sizes, c_int(n), c_longlong(k), _p(ws), _p(res), _s())
+    return res
+
+
+def apply_threshold_masks(tensors, masks, res, k):
+    """Clear mask bytes of the k smallest |w| (ties at the threshold resolved by flat position)."""
+    tie = torch.zeros(1, device=tensors[0].device, dtype=torch.int64)
+    for t, m in zip(tensors, masks):
+        _call("mh_apply_threshold_mask", _p(t), _p(m), c_longlong(t.numel()), _p(res), c_longlong(k), _p(tie), _s())
+
+
+def row_abs_sums(w):
+    out = torch.empty(w.shape[0], device=w.device, dtype=torch.float64)
+    _call("mh_row_abs_sums", _p(w), c_longlong(w.stride(0)), _p(out), c_int(w.shape[0]), c_int(w.shape[1]), _s())
+    return out
+
+
+def col_abs_sums(w):
+    out = torch.empty(w.shape[1], device=w.device, dtype=torch.float64)
+    _call("mh_col_abs_sums", _p(w), c_longlong(w.stride(0)), _p(out), c_int(w.shape[0]), c_int(w.shape[1]), _s())
+    return out
+
+
+# ------------------------------------------------------------------------------ optimizer
+def sumsq_add(x, out):
+    _call("mh_sumsq", _p(x), c_longlong(x.numel()), _p(out), _s())
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, weight_decay=0.0, grad_scale=1.0,
+              max_norm=0.0, sumsq=None, zero_grad=True):
+    _call("mh_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), c_longlong(param.numel()), _f(lr), _f(beta1),
+          _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq), c_int(int(zero_grad)), _s())

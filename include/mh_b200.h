@@ -22,6 +22,13 @@ int mh_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long mh_launch_count(void);
 
+/* Dropout streams: every dropout decision is Philox4x32-10(seed + K * *offset, site, element/8).
+ * `offset` is an optional device-resident counter (NULL disables it) so that CUDA-graph replays
+ * draw fresh masks: bump it once per step with mh_counter_add.  Forward and backward of one step
+ * must see the same counter value. */
+int mh_set_dropout_offset_ptr(const unsigned long long* device_counter);
+int mh_counter_add(unsigned long long* device_counter, unsigned long long v, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * GEMM on tcgen05/TMEM fed by TMA:  D[M,N] = A[M,K] * B[N,K]^T  (+ epilogue)
  * Replaces torch._C._nn.linear at pytorch_code/forward_multihead_attention.py:71-76,110,233
@@ -90,6 +97,11 @@ int mh_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
 int mh_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                      void* dx, void* dx_drop, float* dgamma, float* dbeta, int rows, int cols, float p_in,
                      uint64_t seed_in, uint32_t site_in, float p_out, uint64_t seed_out, uint32_t site_out,
+                     void* stream);
+
+/* y = x * keep-mask / (1 - p), same element indexing as the GEMM epilogues (row * cols + col);
+ * used where a dropout gradient is needed without an adjacent LayerNorm (pre-LN blocks). */
+int mh_dropout_apply(const void* x, void* y, int rows, int cols, float p_drop, uint64_t seed, uint32_t site,
                      void* stream);
 
 /* column sums: out[n] += sum_m x[m, n]  (bias gradients).  x bf16 [rows, ld] */

@@ -16,6 +16,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static const unsigned long long* g_drop_offset = nullptr;
+const unsigned long long* dropout_offset_ptr() { return g_drop_offset; }
+
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long v) { *c += v; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -31,3 +36,16 @@ int sm_count() {
 extern "C" const char* mh_last_error(void) { return mh::g_err; }
 extern "C" int mh_version(void) { return 100; }
 extern "C" long long mh_launch_count(void) { return mh::g_launches; }
+
+/* Device-side 64-bit counter mixed into every dropout seed.  A CUDA graph that replays the same
+ * captured seeds still draws fresh masks each step if it bumps the counter (mh_counter_add). */
+extern "C" int mh_set_dropout_offset_ptr(const unsigned long long* device_counter) {
+  mh::g_drop_offset = device_counter;
+  return 0;
+}
+extern "C" int mh_counter_add(unsigned long long* device_counter, unsigned long long v, void* stream) {
+  mh::counter_add_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(device_counter, v);
+  MH_LAUNCH_CHECK();
+  ++mh::g_launches;
+  return 0;
+}

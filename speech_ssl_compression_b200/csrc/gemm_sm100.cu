@@ -344,12 +344,16 @@ template <int BN, int EPI>
 static int dispatch_major(const mh_gemm_args* a, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d,
                           int grid, cudaStream_t st) {
   if (!a->a_mn && !a->b_mn) return launch<BN, EPI, false, false>(ta, tb, d, grid, st);
-  if (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
-    if (a->a_mn && a->b_mn) return launch<BN, EPI == MH_EPI_F32 ? MH_EPI_F32 : MH_EPI_BF16, true, true>(ta, tb, d, grid, st);
-    if (a->a_mn && !a->b_mn) return launch<BN, EPI == MH_EPI_F32 ? MH_EPI_F32 : MH_EPI_BF16, true, false>(ta, tb, d, grid, st);
-    return launch<BN, EPI == MH_EPI_F32 ? MH_EPI_F32 : MH_EPI_BF16, false, true>(ta, tb, d, grid, st);
+  // dgrad reads the forward weight [N][K] as an MN-major B operand: plain / +add / dGELU outputs
+  if constexpr (EPI == MH_EPI_BF16 || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_F32) {
+    if (!a->a_mn && a->b_mn) return launch<BN, EPI, false, true>(ta, tb, d, grid, st);
   }
-  set_error("MN-major operands are only built for MH_EPI_BF16 / MH_EPI_F32");
+  // wgrad (dW = dY^T X) reads both activations MN-major
+  if constexpr (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
+    if (a->a_mn && a->b_mn) return launch<BN, EPI, true, true>(ta, tb, d, grid, st);
+    if (a->a_mn && !a->b_mn) return launch<BN, EPI, true, false>(ta, tb, d, grid, st);
+  }
+  set_error("operand layout a_mn=%d b_mn=%d is not built for epilogue %d", a->a_mn, a->b_mn, a->epilogue);
   return 1;
 }
 

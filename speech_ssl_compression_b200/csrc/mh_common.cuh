@@ -53,13 +53,16 @@ struct Philox {
 // The forward and the backward regenerate identical decisions from (seed, site, index).
 struct DropCfg {
   uint64_t seed;
+  const unsigned long long* offset;  // optional device counter added to the seed (CUDA-graph replays)
   uint32_t site;    // unique per dropout site (layer * 8 + site id)
   uint32_t thresh;  // 0 => dropout disabled
   float scale;      // 1 / (1 - p)
 };
+const unsigned long long* dropout_offset_ptr();
 __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
   DropCfg d;
   d.seed = seed;
+  d.offset = dropout_offset_ptr();
   d.site = site;
   d.thresh = p > 0.f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u;
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -67,7 +70,8 @@ __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
 }
 // keep-mask bits for the 8 elements [8*group, 8*group+8)
 __device__ __forceinline__ uint32_t drop_keep8(const DropCfg& d, uint64_t group) {
-  uint4 r = Philox(d.seed)(group, d.site);
+  const uint64_t seed = d.seed + (d.offset != nullptr ? 0x9E3779B97F4A7C15ull * __ldg(d.offset) : 0ull);
+  uint4 r = Philox(seed)(group, d.site);
   uint32_t m = 0;
   m |= ((r.x & 0xFFFFu) >= d.thresh) << 0;
   m |= ((r.x >> 16) >= d.thresh) << 1;

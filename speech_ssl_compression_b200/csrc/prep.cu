@@ -190,6 +190,20 @@ __global__ void gather_labels_kernel(const long long* __restrict__ label, const 
   if (i < n_idx) dst[i] = idx[i] >= 0 ? label[idx[i]] : -100;
 }
 
+// y = x * keep(seed, site) / (1 - p), element index = row * cols + col (the GEMM-epilogue indexing)
+__global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long groups,
+                                     DropCfg drop) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    bf16x8_to_f32(ldg128(x + i * 8), v);
+    const uint32_t keep = drop_keep8(drop, static_cast<uint64_t>(i));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1) ? v[j] * drop.scale : 0.f;
+    stg128(y + i * 8, f32_to_bf16x8(v));
+  }
+}
+
 static int ew_grid(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(sm_count()) * 16;
@@ -286,6 +300,16 @@ extern "C" int mh_scatter_rows_add(const void* src, const int* idx, void* dst, i
 extern "C" int mh_gather_labels(const long long* label, const int* idx, long long* dst, int n_idx, void* stream) {
   if (n_idx == 0) return 0;
   gather_labels_kernel<<<(n_idx + 255) / 256, 256, 0, ST>>>(label, idx, dst, n_idx);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}
+
+extern "C" int mh_dropout_apply(const void* x, void* y, int rows, int cols, float p_drop, uint64_t seed, uint32_t site,
+                                void* stream) {
+  MH_CHECK(cols % 8 == 0 && p_drop > 0.f, "dropout_apply: cols %% 8 and p > 0 required");
+  const long long groups = static_cast<long long>(rows) * (cols / 8);
+  dropout_apply_kernel<<<ew_grid(groups, 256), 256, 0, ST>>>(CBF(x), BF(y), groups, make_drop(p_drop, seed, site));
   MH_LAUNCH_CHECK();
   ++g_launches;
   return 0;

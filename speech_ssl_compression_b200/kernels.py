@@ -131,6 +131,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, want_drop=False, p
     return dx, dx_drop
 
 
+def dropout_apply(x, p_drop, seed, site):
+    y = torch.empty_like(x)
+    _call("mh_dropout_apply", _p(x), _p(y), c_int(x.shape[0]), c_int(x.shape[1]), _f(p_drop), c_uint64(seed),
+          c_uint32(site), _s())
+    return y
+
+
 def colsum_add(x, out):
     """out[n] += sum_m x[m, n]  (x bf16 [rows, cols], out fp32 [cols])"""
     _call("mh_colsum", _p(x), c_longlong(x.stride(0)), _p(out), c_int(x.shape[0]), c_int(x.shape[1]), _s())

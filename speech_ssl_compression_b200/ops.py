@@ -1,0 +1,430 @@
+"""Autograd glue between the reference-shaped module tree and the sm_100a kernels.
+
+One ``torch.autograd.Function`` per fused block.  Activations are bf16 ``[B*T, C]`` matrices
+(one row per frame, batch-major); master weights / gradients are fp32.  Weight gradients are
+accumulated **in place** into ``param.grad`` by the wgrad GEMM epilogue (red.add), so gradient
+accumulation over micro-batches and split-K are the same code path, and a data-parallel
+wrapper can all-reduce a layer's gradients as soon as that layer's backward returns.
+
+Dropout is regenerated in the backward from (seed, site, element index); nothing but the
+activations listed in DESIGN.md is saved.
+"""
+import torch
+
+from . import kernels as K
+
+bf16 = torch.bfloat16
+
+# ---------------------------------------------------------------------------------------------
+# weight operand cache: fp32 master (+ prune mask) -> bf16, refreshed when the master changes
+# ---------------------------------------------------------------------------------------------
+_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    """Call after any out-of-band parameter update (raw-pointer optimizer kernels, CUDA graph
+    replays): forces the bf16 operands to be rebuilt on next use."""
+    _EPOCH[0] += 1
+
+
+def param_and_mask(mod, name):
+    """(fp32 Parameter that trains, bool mask or None) for ``mod.<name>`` -- understands the
+    ``<name>_orig`` / ``<name>_mask`` re-parametrisation of pytorch_code.prune."""
+    if name + "_orig" in mod._parameters:
+        return mod._parameters[name + "_orig"], mod._buffers[name + "_mask"]
+    return mod._parameters[name], None
+
+
+def _sig(tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+
+
+def packed_operands(owner, key, linears):
+    """bf16 weight ``[sum N_i, K]`` (rows of the given linears stacked) and fp32 bias
+    ``[sum N_i]`` with prune masks folded in.  Cached on ``owner``."""
+    cache = owner.__dict__.setdefault("_mh_operands", {})
+    parts = []
+    for lin in linears:
+        w, wm = param_and_mask(lin, "weight")
+        b, bm = param_and_mask(lin, "bias")
+        parts.append((w, wm, b, bm))
+    sig = (_EPOCH[0], _sig([t for p in parts for t in p]))
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1], hit[2]
+    n_total = sum(p[0].shape[0] for p in parts)
+    kdim = parts[0][0].shape[1]
+    dev = parts[0][0].device
+    if hit is not None and hit[1].shape == (n_total, kdim):
+        wbuf, bbuf = hit[1], hit[2]
+    else:
+        wbuf = torch.empty(n_total, kdim, device=dev, dtype=bf16)
+        bbuf = torch.empty(n_total, device=dev, dtype=torch.float32)
+    with torch.no_grad():
+        r = 0
+        for w, wm, b, bm in parts:
+            n = w.shape[0]
+            K.weight_prep(w.detach(), wm, wbuf[r:r + n])
+            K.bias_prep(b.detach(), bm, bbuf[r:r + n])
+            r += n
+    cache[key] = (sig, wbuf, bbuf)
+    return wbuf, bbuf
+
+
+def _grad_of(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def _wgrad(dy, x, lin, col0=0, ncols=None):
+    """lin.weight.grad += dy[:, col0:col0+n]^T @ x  (masked);  lin.bias.grad += column sums."""
+    w, wm = param_and_mask(lin, "weight")
+    b, bm = param_and_mask(lin, "bias")
+    n = w.shape[0] if ncols is None else ncols
+    dyv = dy[:, col0:col0 + n] if (col0 or n != dy.shape[1]) else dy
+    if w.requires_grad:
+        K.gemm(dyv, x, _grad_of(w), a_mn=True, b_mn=True, epilogue=K.EPI_F32, mask=wm)
+    if b is not None and b.requires_grad:
+        g = _grad_of(b)
+        if bm is None:
+            K.colsum_add(dyv, g)
+        else:
+            tmp = torch.zeros_like(g)
+            K.colsum_add(dyv, tmp)
+            g.add_(tmp * bm)
+
+
+# ---------------------------------------------------------------------------------------------
+# plain linear (pre_extract_proj, final_proj, prediction heads)
+# ---------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lin, *params):
+        w, bias = packed_operands(lin, "self", [lin])
+        out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=bf16)
+        K.gemm(x, w, out, bias=bias)
+        ctx.lin = lin
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        _wgrad(dy, x, ctx.lin)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            K.gemm(dy, w, dx, b_mn=True)
+        return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+def linear(x, lin):
+    """y = x @ W^T + b on the tcgen05 GEMM.  x: bf16 [rows, in_features]."""
+    return LinearFn.apply(x, lin, *[p for p in lin.parameters()])
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm (+ output dropout) -- encoder-level LN (module.py:232-236)
+# ---------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln, p_drop, seed, site, gamma, beta):
+        y, mean, rstd = K.layernorm_fwd(x, gamma.detach(), beta.detach(), ln.eps, p_drop=p_drop, seed=seed, site=site)
+        ctx.ln, ctx.drop = ln, (p_drop, seed, site)
+        ctx.save_for_backward(x, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        ln = ctx.ln
+        p, seed, site = ctx.drop
+        dx, _ = K.layernorm_bwd(dy.contiguous(), x, ln.weight.detach(), mean, rstd, _grad_of(ln.weight), _grad_of(ln.bias),
+                                p_in=p, seed_in=seed, site_in=site)
+        return dx, None, None, None, None, None, None
+
+
+def layer_norm(x, ln, p_drop=0.0, seed=0, site=0):
+    return LayerNormFn.apply(x, ln, p_drop, seed, site, ln.weight, ln.bias)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused transformer encoder layer (module.py:82-133 + multihead_attention.py:98-172 +
+# forward_multihead_attention.py:39-243)
+# ---------------------------------------------------------------------------------------------
+SITE_ATTN, SITE_DROP1, SITE_DROP2, SITE_DROP3 = 0, 1, 2, 3
+
+
+class EncoderLayerFn(torch.autograd.Function):
+    """x [B*T, C] bf16 -> layer output [B*T, C] bf16 (post-LN or pre-LN block)."""
+
+    @staticmethod
+    def forward(ctx, x, kv_len, layer, B, T, seed, site_base, causal, *params):
+        mha = layer.self_attn
+        heads = mha.num_heads
+        training = layer.training
+        p_res = layer.dropout1.p if training else 0.0
+        p_act = layer.dropout2.p if training else 0.0
+        p_att = mha.dropout_module.p if (training or mha.dropout_module.apply_during_inference) else 0.0
+        pre_ln = layer.layer_norm_first
+        ln1, ln2 = layer.self_attn_layer_norm, layer.final_layer_norm
+        M, C = x.shape
+        dev = x.device
+        wqkv, bqkv = packed_operands(mha, "qkv", [mha.q_proj, mha.k_proj, mha.v_proj])
+        wo, bo = packed_operands(mha, "out", [mha.out_proj])
+        w1, b1 = packed_operands(layer, "fc1", [layer.fc1])
+        w2, b2 = packed_operands(layer, "fc2", [layer.fc2])
+        E, F = wo.shape[1], w1.shape[0]
+
+        mean0 = rstd0 = None
+        a_in = x
+        if pre_ln:
+            a_in, mean0, rstd0 = K.layernorm_fwd(x, ln1.weight.detach(), ln1.bias.detach(), ln1.eps)
+        qkv = torch.empty(M, 3 * E, device=dev, dtype=bf16)
+        K.gemm(a_in, wqkv, qkv, bias=bqkv)
+        ctxv, lse = K.attn_fwd(qkv, kv_len, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site_base + SITE_ATTN)
+        y1 = torch.empty(M, C, device=dev, dtype=bf16)
+        K.gemm(ctxv, wo, y1, epilogue=K.EPI_RES, bias=bo, aux_in=x, p_drop=p_res, seed=seed, site=site_base + SITE_DROP1)
+        if pre_ln:
+            f_in, mean1, rstd1 = K.layernorm_fwd(y1, ln2.weight.detach(), ln2.bias.detach(), ln2.eps)
+            res2 = y1
+        else:
+            f_in, mean1, rstd1 = K.layernorm_fwd(y1, ln1.weight.detach(), ln1.bias.detach(), ln1.eps)
+            res2 = f_in
+        pre = torch.empty(M, F, device=dev, dtype=bf16)
+        u = torch.empty(M, F, device=dev, dtype=bf16)
+        K.gemm(f_in, w1, u, epilogue=K.EPI_GELU, bias=b1, aux_out=pre, p_drop=p_act, seed=seed, site=site_base + SITE_DROP2)
+        y2 = torch.empty(M, C, device=dev, dtype=bf16)
+        K.gemm(u, w2, y2, epilogue=K.EPI_RES, bias=b2, aux_in=res2, p_drop=p_res, seed=seed, site=site_base + SITE_DROP3)
+        if pre_ln:
+            out, mean2, rstd2 = y2, None, None
+        else:
+            out, mean2, rstd2 = K.layernorm_fwd(y2, ln2.weight.detach(), ln2.bias.detach(), ln2.eps)
+
+        if any(ctx.needs_input_grad):
+            ctx.layer = layer
+            ctx.meta = (B, T, heads, seed, site_base, causal, p_res, p_act, p_att, pre_ln)
+            ctx.save_for_backward(x, kv_len, a_in, qkv, ctxv, lse, y1, mean0, rstd0, mean1, rstd1, f_in, pre, u, y2, mean2,
+                                  rstd2, wqkv, wo, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, kv_len, a_in, qkv, ctxv, lse, y1, mean0, rstd0, mean1, rstd1, f_in, pre, u, y2, mean2, rstd2, wqkv, wo, w1,
+         w2) = ctx.saved_tensors
+        layer = ctx.layer
+        mha = layer.self_attn
+        B, T, heads, seed, site_base, causal, p_res, p_act, p_att, pre_ln = ctx.meta
+        ln1, ln2 = layer.self_attn_layer_norm, layer.final_layer_norm
+        E = wo.shape[1]
+        dout = dout.contiguous()
+        s1, s2, s3 = site_base + SITE_DROP1, site_base + SITE_DROP2, site_base + SITE_DROP3
+
+        # ---- FFN block ----
+        if pre_ln:
+            # out = y1 + drop3(fc2(u));  dz2 = dout * mask3, residual gradient = dout
+            dy2 = dout
+            dz2 = K.dropout_apply(dout, p_res, seed, s3) if p_res > 0.0 else dout
+        else:
+            dy2, dz2 = K.layernorm_bwd(dout, y2, ln2.weight.detach(), mean2, rstd2, _grad_of(ln2.weight), _grad_of(ln2.bias),
+                                       want_drop=p_res > 0.0, p_out=p_res, seed_out=seed, site_out=s3)
+            if dz2 is None:
+                dz2 = dy2
+        _wgrad(dz2, u, layer.fc2)
+        dpre = torch.empty_like(pre)
+        K.gemm(dz2, w2, dpre, b_mn=True, epilogue=K.EPI_DGELU, aux_in=pre, p_drop=p_act, seed=seed, site=s2)
+        _wgrad(dpre, f_in, layer.fc1)
+        if pre_ln:
+            # f_in = LN2(y1): d y1 = dy2 (residual) + LN2_bwd(dpre W1)
+            df = torch.empty_like(f_in)
+            K.gemm(dpre, w1, df, b_mn=True)
+            dln, _ = K.layernorm_bwd(df, y1, ln2.weight.detach(), mean1, rstd1, _grad_of(ln2.weight), _grad_of(ln2.bias))
+            dy1 = dln + dy2
+            dz1 = K.dropout_apply(dy1, p_res, seed, s1) if p_res > 0.0 else dy1
+        else:
+            dx1 = torch.empty_like(f_in)
+            K.gemm(dpre, w1, dx1, b_mn=True, epilogue=K.EPI_ADD, aux_in=dy2)
+            dy1, dz1 = K.layernorm_bwd(dx1, y1, ln1.weight.detach(), mean1, rstd1, _grad_of(ln1.weight), _grad_of(ln1.bias),
+                                       want_drop=p_res > 0.0, p_out=p_res, seed_out=seed, site_out=s1)
+            if dz1 is None:
+                dz1 = dy1
+        # ---- attention block ----
+        _wgrad(dz1, ctxv, mha.out_proj)
+        dctx = torch.empty_like(ctxv)
+        K.gemm(dz1, wo, dctx, b_mn=True)
+        dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, B, T, heads, causal=causal, p_drop=p_att, seed=seed,
+                          site=site_base + SITE_ATTN)
+        for i, lin in enumerate((mha.q_proj, mha.k_proj, mha.v_proj)):
+            _wgrad(dqkv, a_in, lin, col0=i * E, ncols=E)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if pre_ln:
+                da = torch.empty_like(x)
+                K.gemm(dqkv, wqkv, da, b_mn=True)
+                dln, _ = K.layernorm_bwd(da, x, ln1.weight.detach(), mean0, rstd0, _grad_of(ln1.weight), _grad_of(ln1.bias))
+                dx = dln + dy1
+            else:
+                K.gemm(dqkv, wqkv, dx, b_mn=True, epilogue=K.EPI_ADD, aux_in=dy1)
+        hook = getattr(layer, "_mh_grad_ready_hook", None)
+        if hook is not None:
+            hook(layer)
+        return (dx,) + (None,) * (len(ctx.needs_input_grad) - 1)
+
+
+def encoder_layer(x, kv_len, layer, B, T, seed, site_base, causal=False):
+    params = [p for p in layer.parameters()]
+    return EncoderLayerFn.apply(x, kv_len, layer, B, T, seed, site_base, causal, *params)
+
+
+# ---------------------------------------------------------------------------------------------
+# dtype / layout boundary
+# ---------------------------------------------------------------------------------------------
+class MaskRowsToBf16(torch.autograd.Function):
+    """bf16(x) with selected rows zeroed (model.py:80 masking, module.py:226-227 padding)."""
+
+    @staticmethod
+    def forward(ctx, x, zero_row):
+        ctx.save_for_backward(zero_row)
+        return K.mask_rows_to_bf16(x, zero_row)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (zero_row,) = ctx.saved_tensors
+        g = K.to_f32(dy)
+        if zero_row is not None:
+            g = g.masked_fill(zero_row.bool().unsqueeze(1), 0.0)
+        return g, None
+
+
+class ZeroRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, zero_row):
+        ctx.save_for_backward(zero_row)
+        ctx.mark_dirty(x)
+        K.zero_rows_(x, zero_row)
+        return x
+
+    @staticmethod
+    def backward(ctx, dy):
+        (zero_row,) = ctx.saved_tensors
+        dy = dy.contiguous().clone()
+        K.zero_rows_(dy, zero_row)
+        return dy, None
+
+
+class ToF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.to_f32(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.to_bf16(dy)
+
+
+class GatherRows(torch.autograd.Function):
+    """hidden[masked_indices] (model.py:148): rows listed in ``idx`` (row-major (b, t) order)."""
+
+    @staticmethod
+    def forward(ctx, x, idx, n_idx):
+        ctx.save_for_backward(idx)
+        ctx.shape, ctx.n_idx = x.shape, n_idx
+        return K.gather_rows(x, idx, n_idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        dx = torch.zeros(ctx.shape, device=dy.device, dtype=bf16)
+        K.scatter_rows_add_(dy.contiguous(), idx, ctx.n_idx, dx)
+        return dx, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# criteria
+# ---------------------------------------------------------------------------------------------
+class CrossEntropyFn(torch.autograd.Function):
+    """CrossEntropyLoss(ignore_index=-100, reduction='mean') on bf16 logits, fused fwd + bwd.
+
+    ``n_valid`` (device int32 [1], optional) limits the rows that count -- lets a statically
+    shaped, CUDA-graph-captured step use a padded row list.  ``reduce_fn`` (optional) is
+    applied to the device accumulator [sum_loss, count] before the mean is formed: a
+    data-parallel wrapper passes an all-reduce there so the normaliser is the *global*
+    masked-frame count, matching nn.DataParallel's gather-then-mean semantics."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, n_valid, reduce_fn):
+        acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+        K.ce_fwd(logits, labels, acc, n_valid=n_valid)
+        local = acc.clone()
+        if reduce_fn is not None:
+            reduce_fn(acc)
+        out = torch.empty(2, device=logits.device, dtype=torch.float32)  # [loss, grad_scale]
+        K.ce_finalize(acc, weight, out[0:1], out[1:2])
+        ctx.save_for_backward(logits, labels, n_valid, out)
+        ctx.local_acc = local
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, n_valid, out = ctx.saved_tensors
+        gs = out[1:2] * dloss.reshape(1).to(torch.float32)
+        return K.ce_bwd(logits, labels, gs, n_valid=n_valid), None, None, None, None
+
+
+def cross_entropy(logits, labels, weight=1.0, n_valid=None, reduce_fn=None):
+    return CrossEntropyFn.apply(logits, labels, float(weight), n_valid, reduce_fn)
+
+
+class KDLossFn(torch.autograd.Function):
+    """(1-alpha) * CE(student, label) + alpha * KLDiv_batchmean(log_softmax(s/T), softmax(t/T))
+    (distillation/pretrain_expert.py:83-92).  Returns [total, hard, soft, teacher_ce]."""
+
+    @staticmethod
+    def forward(ctx, s_logits, t_logits, labels, T, alpha, n_valid, reduce_fn):
+        acc = torch.zeros(5, device=s_logits.device, dtype=torch.float32)
+        K.kd_fwd(s_logits, t_logits, labels, T, acc, n_valid=n_valid)
+        if reduce_fn is not None:
+            reduce_fn(acc)
+        out = torch.empty(6, device=s_logits.device, dtype=torch.float32)
+        K.kd_finalize(acc, alpha, out[0:4], out[4:5], out[5:6])
+        ctx.save_for_backward(s_logits, t_logits, labels, n_valid, out)
+        ctx.T = T
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out[0:4]
+
+    @staticmethod
+    def backward(ctx, dloss, _):
+        s_logits, t_logits, labels, n_valid, out = ctx.saved_tensors
+        d = dloss.reshape(1).to(torch.float32)
+        return (K.kd_bwd(s_logits, t_logits, labels, ctx.T, out[4:5] * d, out[5:6] * d, n_valid=n_valid), None, None, None,
+                None, None, None)
+
+
+def kd_loss(s_logits, t_logits, labels, T=1.0, alpha=0.5, n_valid=None, reduce_fn=None):
+    return KDLossFn.apply(s_logits, t_logits, labels, float(T), float(alpha), n_valid, reduce_fn)
+
+
+class L1CosFn(torch.autograd.Function):
+    """mean |p - t| + w_cos * mean(-logsigmoid(cos(p, t))) over rows of bf16 [rows, C]."""
+
+    @staticmethod
+    def forward(ctx, pred, target, cos_weight):
+        rows, cols = pred.shape
+        acc = torch.zeros(2, device=pred.device, dtype=torch.float32)
+        K.l1cos_fwd(pred, target, acc)
+        ctx.save_for_backward(pred, target)
+        ctx.w = (1.0 / (rows * cols), cos_weight / rows)
+        return acc[0] * ctx.w[0] + acc[1] * ctx.w[1]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred, target = ctx.saved_tensors
+        d = dloss.reshape(1).to(torch.float32)
+        return K.l1cos_bwd(pred, target, d * ctx.w[0], d * ctx.w[1]), None, None
+
+
+def l1_cosine_loss(pred, target, cos_weight=1.0):
+    return L1CosFn.apply(pred, target, float(cos_weight))

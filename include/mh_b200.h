@@ -201,7 +201,7 @@ int mh_col_abs_sums(const float* w, long long ld, double* out, int rows, int col
  * ------------------------------------------------------------------------------------- */
 int mh_sumsq(const float* x, long long n, float* out, void* stream);
 int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                 float beta2, float eps, float weight_decay, const int* step /* device */, float grad_scale,
+                 float beta2, float eps, float weight_decay, const unsigned long long* step /* device, 1-based */, float grad_scale,
                  float max_norm, const float* sumsq, int zero_grad, void* stream);
 
 #ifdef __cplusplus

@@ -131,12 +131,13 @@ kd_fwd_kernel(const __nv_bfloat16* __restrict__ s_logits, const __nv_bfloat16* _
   const int nchunks = n_class >> 3;
   float a_hard = 0.f, a_cnt = 0.f, a_soft = 0.f, a_tce = 0.f, a_rows = 0.f;
   for (int row = blockIdx.x * CR_WARPS + (threadIdx.x >> 5); row < limit; row += gridDim.x * CR_WARPS) {
+    const long long lab = labels[row];
+    if (lab < 0) continue;  // padded slot of a statically shaped row list
     float s[NCH][8], t[NCH][8];
     load_row<NCH>(s_logits + static_cast<long long>(row) * n_class, nchunks, lane, s, -INFINITY);
     load_row<NCH>(t_logits + static_cast<long long>(row) * n_class, nchunks, lane, t, -INFINITY);
     const float ms = row_max<NCH>(s), mt = row_max<NCH>(t);
-    const long long lab = labels[row];
-    if (lab >= 0) {
+    {
       a_hard += ms + __logf(row_sumexp<NCH>(s, ms, 1.f)) - pick<NCH>(s, lane, static_cast<int>(lab));
       a_tce += mt + __logf(row_sumexp<NCH>(t, mt, 1.f)) - pick<NCH>(t, lane, static_cast<int>(lab));
       a_cnt += 1.f;
@@ -177,7 +178,7 @@ kd_bwd_kernel(const __nv_bfloat16* __restrict__ s_logits, const __nv_bfloat16* _
   const float wh = *w_hard, ws = *w_soft * inv_t;
   for (int row = blockIdx.x * CR_WARPS + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * CR_WARPS) {
     __nv_bfloat16* out = dlogits + static_cast<long long>(row) * n_class;
-    if (row >= limit) {
+    if (row >= limit || labels[row] < 0) {
 #pragma unroll
       for (int i = 0; i < NCH; ++i)
         if (lane + 32 * i < nchunks) stg128(out + (lane + 32 * i) * 8, make_uint4(0, 0, 0, 0));

@@ -31,9 +31,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-            float lr, float b1, float b2, float eps, float wd, const int* __restrict__ step_ptr, float grad_scale,
+            float lr, float b1, float b2, float eps, float wd, const unsigned long long* __restrict__ step_ptr, float grad_scale,
             float max_norm, const float* __restrict__ sumsq, int zero_grad) {
-  const int step = *step_ptr;
+  const float step = static_cast<float>(*step_ptr);
   float clip = 1.f;
   bool skip = false;
   if (sumsq != nullptr) {
@@ -42,8 +42,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
     if (max_norm > 0.f) clip = fminf(1.f, max_norm / (norm + 1e-6f));
   }
   const float gs = grad_scale * clip;
-  const float bc1 = 1.f - powf(b1, static_cast<float>(step));
-  const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2 = 1.f - powf(b2, step);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -87,7 +87,7 @@ extern "C" int mh_sumsq(const float* x, long long n, float* out, void* stream) {
 }
 
 extern "C" int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                            float beta1, float beta2, float eps, float weight_decay, const int* step, float grad_scale,
+                            float beta1, float beta2, float eps, float weight_decay, const unsigned long long* step, float grad_scale,
                             float max_norm, const float* sumsq, int zero_grad, void* stream) {
   MH_CHECK(n % 4 == 0, "adam: flat buffer length must be a multiple of 4 (got %lld)", n);
   if (n == 0) return 0;

@@ -299,3 +299,12 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, 
               max_norm=0.0, sumsq=None, zero_grad=True):
     _call("mh_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), c_longlong(param.numel()), _f(lr), _f(beta1),
           _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq), c_int(int(zero_grad)), _s())
+
+
+def set_dropout_offset(counter):
+    """Register a device uint64 counter that is mixed into every dropout seed (None disables)."""
+    _call("mh_set_dropout_offset_ptr", _p(counter))
+
+
+def counter_add(counter, v=1):
+    _call("mh_counter_add", _p(counter), c_uint64(v), _s())

@@ -48,7 +48,8 @@ def packed_operands(owner, key, linears):
         w, wm = param_and_mask(lin, "weight")
         b, bm = param_and_mask(lin, "bias")
         parts.append((w, wm, b, bm))
-    sig = (_EPOCH[0], _sig([t for p in parts for t in p]))
+    trainable = any(t is not None and t.requires_grad for p in parts for t in p)
+    sig = (_EPOCH[0] if trainable else -1, _sig([t for p in parts for t in p]))
     hit = cache.get(key)
     if hit is not None and hit[0] == sig:
         return hit[1], hit[2]

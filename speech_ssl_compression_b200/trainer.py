@@ -1,0 +1,187 @@
+"""Training-step driver: flat parameter storage, the fused Adam step and an optional
+CUDA-graph capture of one whole optimizer step (forward + backward + gradient all-reduce +
+clip + Adam), which removes Python / launch overhead from the hot loop.
+
+Mirrors what reference ``runner.py:357-427`` does per optimizer step: forward -> loss / accum
+-> backward -> grads /= n -> clip_grad_norm_ -> Adam.step -> zero_grad.
+"""
+import numpy as np
+import torch
+
+from . import kernels as K
+from . import ops
+from .parallel import DataParallelB200, FlatBuffers
+
+
+class FusedAdam:
+    """Adam over the flat fp32 buffers in one HBM pass (``mh_adam_step``): grad scaling,
+    global-norm clipping (norm from ``mh_sumsq``), moment updates, parameter update and
+    gradient zeroing.  Numerically the same update rule as ``torch.optim.Adam``."""
+
+    def __init__(self, flat: FlatBuffers, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.flat = flat
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), tuple(betas), float(eps), float(weight_decay)
+        self.exp_avg = torch.zeros_like(flat.flat_param)
+        self.exp_avg_sq = torch.zeros_like(flat.flat_param)
+        self.step_count = torch.zeros(1, device=flat.flat_param.device, dtype=torch.int64)
+        self.sumsq = torch.zeros(1, device=flat.flat_param.device, dtype=torch.float32)
+
+    def step(self, grad_scale=1.0, max_norm=0.0):
+        K.counter_add(self.step_count, 1)
+        self.sumsq.zero_()
+        K.sumsq_add(self.flat.flat_grad, self.sumsq)
+        K.adam_step(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                    lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
+                    grad_scale=grad_scale, max_norm=max_norm, sumsq=self.sumsq, zero_grad=True)
+        ops.bump_weight_epoch()
+
+    def grad_norm(self, grad_scale=1.0):
+        return float(self.sumsq.sqrt().item()) * grad_scale
+
+    def zero_grad(self):
+        self.flat.flat_grad.zero_()
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count.copy_(sd["step"])
+
+
+def trainable_params(expert):
+    """Layer-contiguous parameter order (so each encoder layer is one all-reduce bucket)."""
+    seen, out = set(), []
+    for p in expert.parameters():
+        if p.requires_grad and id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
+class TrainStep:
+    """One optimizer step of an expert (pre-training / pruning fine-tune / distillation) on a
+    statically shaped batch, eager or CUDA-graph captured.
+
+    Static device buffers: feat (B,T,D) f32, label (B,T) i64, pad_mask (B,T) f32, span mask
+    (B,T) bool.  ``load_batch`` does the host->device copies (from pinned memory) and draws the
+    span mask on the host exactly like the reference (NumPy global stream, including the
+    per-layer layer-drop draws that shift the stream)."""
+
+    def __init__(self, expert, B, T, D, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=10.0,
+                 use_graph=True, device="cuda"):
+        self.expert, self.B, self.T, self.D = expert, B, T, D
+        self.device = torch.device(device)
+        self.max_norm = max_norm
+        self.model = expert.model
+        self.model.static_rows = True
+        self.teacher = getattr(expert, "teacher_model", None)
+        if self.teacher is not None:
+            self.teacher.static_rows = True
+        self.flat = FlatBuffers(trainable_params(expert))
+        self.opt = FusedAdam(self.flat, lr, betas, eps, weight_decay)
+        self.dp = getattr(expert, "dp", None)
+        if self.dp is not None:
+            self.dp.attach(self.flat)
+        dev = self.device
+        self.feat = torch.zeros(B, T, D, device=dev)
+        self.label = torch.zeros(B, T, device=dev, dtype=torch.int64)
+        self.pad = torch.ones(B, T, device=dev)
+        self.mask = torch.zeros(B, T, device=dev, dtype=torch.bool)
+        self.loss = torch.zeros(1, device=dev)
+        self.h_mask = torch.zeros(B, T, dtype=torch.bool).pin_memory()
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.rng_counter = torch.zeros(1, device=dev, dtype=torch.int64)
+        K.set_dropout_offset(self.rng_counter)
+        self.use_graph = use_graph
+        self.graph = None
+        self.n_layerdrop_draws = self.model.model_config.encoder_layers + (
+            self.teacher.model_config.encoder_layers if self.teacher is not None else 0)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------------------------------
+    def draw_mask(self, lens):
+        cfg = (self.teacher or self.model).model_config
+        from .fairseq_code import compute_mask_indices
+
+        m = compute_mask_indices((self.B, self.T), None, cfg.mask_prob, cfg.mask_length, cfg.mask_selection,
+                                 cfg.mask_other, min_masks=2, no_overlap=cfg.no_mask_overlap,
+                                 min_space=cfg.mask_min_space, require_same_masks=False, valid_lens=lens)
+        return m
+
+    def load_batch(self, feat, label, pad, lens, masking=True):
+        """feat / label / pad: pinned host tensors.  Copies are asynchronous on the current stream."""
+        self.feat.copy_(feat, non_blocking=True)
+        self.label.copy_(label, non_blocking=True)
+        self.pad.copy_(pad, non_blocking=True)
+        nbytes = feat.numel() * 4 + label.numel() * 8 + pad.numel() * 4
+        if masking:
+            self.h_mask.copy_(torch.from_numpy(self.draw_mask(lens)))
+            self.mask.copy_(self.h_mask, non_blocking=True)
+            nbytes += self.h_mask.numel()
+        self.h2d_bytes = nbytes
+        self._lens = list(lens)
+
+    def _body(self):
+        K.counter_add(self.rng_counter, 1)
+        data = (self.feat, self.label, self.pad, None)
+        self._patch_mask(True)
+        try:
+            loss, _ = self.expert(data)
+        finally:
+            self._patch_mask(False)
+        loss.backward()
+        if self.dp is not None:
+            self.dp.finish()
+        self.loss.copy_(loss.detach().reshape(1))
+        self.opt.step(grad_scale=1.0, max_norm=self.max_norm)
+
+    def _patch_mask(self, on):
+        """Feed the pre-drawn device mask through the model's ``teacher_mask_indices`` door so no
+        host RNG / H2D copy happens inside the (capturable) step body."""
+        first = self.teacher or self.model
+        if on:
+            mask = self.mask
+            self._orig_draw = first._draw_mask
+            first._draw_mask = lambda B, T, lens, pm, tmi, dev: (tmi if tmi is not None else mask)
+        else:
+            first._draw_mask = self._orig_draw
+
+    def capture(self, warmup=2):
+        """Warm up eagerly on a side stream, then capture one step into a CUDA graph."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        ops.bump_weight_epoch()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = K.L.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = K.L.launch_count() - n0
+        return self
+
+    def run(self):
+        """Execute one optimizer step on the currently loaded batch; returns nothing (loss is in
+        ``self.loss`` on the device; ``read_loss`` fetches it)."""
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            for _ in range(self.n_layerdrop_draws):
+                np.random.random()  # a replay skips the per-layer host draws of the eager forward (module.py:243)
+            self.graph.replay()
+        else:
+            n0 = K.L.launch_count()
+            self._body()
+            self.launches_per_step = K.L.launch_count() - n0
+
+    def read_loss(self):
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = 4
+        return float(self.h_loss[0])

@@ -1,20 +1,24 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T   bf16 x bf16 -> fp32 (TMEM) -> fused epilogue
+//   D[M,N] = A[M,K] * B[N,K]^T   bf16 x bf16 -> fp32 (TMEM) -> fused epilogue -> TMA store
 //
-// Roles (320 threads, one CTA per SM):
-//   warps 0-7 : epilogue.  warp w reads TMEM lanes 32*(w%4)..+31 (one accumulator row per
-//               thread) and the column half (w/4) of the tile; bias / GELU / dropout /
-//               residual / mask are applied in fp32 registers; 16-byte global stores.
-//   warp 8    : TMA producer (one elected lane): 128B-swizzled tiles of A and B into a
-//               4- or 6-stage shared-memory ring, mbarrier complete_tx signalling.
-//   warp 9    : TMEM allocator + MMA issuer (one elected lane): tcgen05.mma 128 x BN x 16,
-//               accumulators double buffered in TMEM so the epilogue of tile i overlaps the
-//               main loop of tile i+1; tcgen05.commit releases smem stages / publishes tiles.
-// Operands may be K-major (row = m or n, 64 contiguous k) or MN-major (row = k, 64 contiguous
-// m or n); the latter is what wgrad (dW = dY^T X) needs and avoids any transpose kernel.
-// MH_EPI_F32 accumulates with red.global.add.f32, which makes split-K and gradient
-// accumulation the same code path.
+// Roles (576 threads, one CTA per SM):
+//   warps 0-15 : epilogue, 4 column groups x 4 TMEM lane quadrants.  Warp w owns accumulator rows
+//                32*(w%4)..+31 (one row per thread) and the columns of group w/4 (BN/4 wide).  Values are
+//                pulled with tcgen05.ld, bias / GELU / dropout / residual / prune-mask are applied in fp32
+//                registers, and the result is written into the group's 128-row staging tile in shared
+//                memory (hardware swizzle pattern -> conflict-free 16-byte stores).  One elected thread per
+//                group then issues a TMA tile store (or fp32 reduce-add for weight gradients), so HBM sees
+//                full 128-byte lines and ragged M / N edges are clipped by the hardware.  Residual /
+//                pre-activation inputs arrive the same way: TMA load into the staging tile, modified in place.
+//   warp 16    : TMA producer (one elected lane): 128B-swizzled tiles of A and B into a 3- or 5-stage
+//                shared-memory ring, mbarrier complete_tx signalling.
+//   warp 17    : TMEM allocator + MMA issuer (one elected lane): tcgen05.mma 128 x BN x 16, accumulators
+//                double buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1;
+//                tcgen05.commit releases smem stages / publishes tiles.
+// Operands may be K-major (row = m or n, 64 contiguous k) or MN-major (row = k, 64 contiguous m or n); the
+// latter is what wgrad (dW = dY^T X) needs and avoids any transpose kernel.  MH_EPI_F32 accumulates with
+// cp.reduce.async.bulk (.add.f32), which makes split-K and gradient accumulation the same code path.
 #include "mh_b200.h"
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
@@ -23,50 +27,62 @@ namespace mh {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int PRODUCER_WARP = 8;
-constexpr int MMA_WARP = 9;
-constexpr int GEMM_THREADS = 320;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_GROUPS = 4;
+constexpr int PRODUCER_WARP = 16;
+constexpr int MMA_WARP = 17;
+constexpr int GEMM_THREADS = 576;
+constexpr int STG_CHUNK = 128 * 128;  // staging bytes per column group: 128 rows x (64 or 128) B
 
 template <int BN>
 struct TileCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = BN == 256 ? 3 : 5;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + EPI_GROUPS * STG_CHUNK + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
 };
 
 struct GemmDev {
   int M, N, K;
-  void* D;
   long long ldd;
   const float* bias;
-  const __nv_bfloat16* aux_in;
-  __nv_bfloat16* aux_out;
-  long long ld_aux;
+  int has_aux_out;
   const uint8_t* mask;
   DropCfg drop;
   int split_k;
 };
 
-__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// byte offset of 16-byte chunk `ch` of row `r` in a staging tile whose rows are ROWB bytes, laid out the
+// way TMA expects for CU_TENSOR_MAP_SWIZZLE_128B (ROWB = 128) / SWIZZLE_64B (ROWB = 64)
+template <int ROWB>
+__device__ __forceinline__ uint32_t stg_off(int r, int ch) {
+  if (ROWB == 128) return r * 128 + ((ch ^ (r & 7)) << 4);
+  return r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
 }
 
 template <int BN, int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
+            const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
   using Cfg = TileCfg<BN>;
+  constexpr bool OUT_F32 = EPI == MH_EPI_F32;
+  constexpr bool HAS_AUX_IN = EPI == MH_EPI_RES || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD;
+  constexpr int CG = BN / EPI_GROUPS;              // columns per epilogue group
+  constexpr int ROWB = CG * (OUT_F32 ? 4 : 2);     // staging row bytes
+  static_assert(ROWB == 64 || ROWB == 128, "fp32 output needs BN = 128");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_GROUPS * STG_CHUNK);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* aux_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + EPI_GROUPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,6 +90,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -82,6 +99,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], EPI_WARPS);
     }
+    for (int s = 0; s < EPI_GROUPS; ++s) mbar_init(&aux_full[s], 1);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -173,95 +191,143 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ------------------------------------------------------------- epilogue warps
     const int quad = warp & 3;         // TMEM lane quadrant
-    const int half = warp >> 2;        // column half of the tile
-    const int row_in_tile = quad * 32 + lane;
-    constexpr int kChunksPerHalf = BN / 64;  // 32-column chunks per half
+    const int grp = warp >> 2;         // column group
+    const int r_tile = quad * 32 + lane;
+    const bool leader = quad == 0 && lane == 0;
+    uint8_t* stg = staging + grp * STG_CHUNK;
+    const int bar_id = 1 + grp;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile / splits;
       const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
       const int kb0 = (tile % splits) * kb_per_split;
       const bool has_k = kb0 < kblocks_total;  // empty split (possible when splits does not divide)
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const long long row = m0 + row_in_tile;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c = 0; c < kChunksPerHalf; ++c) {
-        const int col_in_tile = half * (BN / 2) + c * 32;
-        const int col0 = n0 + col_in_tile;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_in_tile, r);
-        tmem_ld_wait();
-        if (!row_ok || !has_k) continue;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int col = col0 + q * 8;
-          if (col >= p.N) break;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
-          if (EPI == MH_EPI_F32) {
-            float* dst = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
-            if (p.mask != nullptr) {
-              const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + row * p.ldd + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (((mk.x >> (8 * j)) & 0xFF) == 0) v[j] = 0.f;
-                if (((mk.y >> (8 * j)) & 0xFF) == 0) v[4 + j] = 0.f;
-              }
-            }
-            red_add_f32x4(dst, v[0], v[1], v[2], v[3]);
-            red_add_f32x4(dst + 4, v[4], v[5], v[6], v[7]);
-            continue;
-          }
-          if (EPI == MH_EPI_BF16 || EPI == MH_EPI_GELU || EPI == MH_EPI_RES) {
-            if (p.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-          }
-          if (EPI == MH_EPI_GELU) {
-            // the reference evaluates GELU in fp32 on the half-precision fc1 output
-            // (fairseq_code/gelu.py:35 under autocast): round first, then activate.
-            uint4 pre = f32_to_bf16x8(v);
-            if (p.aux_out != nullptr) stg128(p.aux_out + row * p.ld_aux + col, pre);
-            bf16x8_to_f32(pre, v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (EPI == MH_EPI_DGELU) {
-            float pre[8];
-            bf16x8_to_f32(ldg128(p.aux_in + row * p.ld_aux + col), pre);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
-          }
-          if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
-            if (p.drop.thresh != 0) {
-              const uint64_t group = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + (col >> 3);
-              const uint32_t keep = drop_keep8(p.drop, group);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1) ? v[j] * p.drop.scale : 0.f;
-            }
-          }
-          if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
-            float a[8];
-            bf16x8_to_f32(ldg128(p.aux_in + row * p.ld_aux + col), a);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += a[j];
-          }
-          stg128(reinterpret_cast<__nv_bfloat16*>(p.D) + row * p.ldd + col, f32_to_bf16x8(v));
+      const int gcol0 = n0 + grp * CG;
+      const bool active = gcol0 < p.N && has_k;  // uniform over the group
+      const long long row = m0 + r_tile;
+
+      // (1) the staging tile is free once the previous TMA store has read it; residual / pre-activation
+      //     tiles are fetched into it right away so the load overlaps the wait for the accumulator
+      if (leader) {
+        bulk_wait_read0();
+        if (HAS_AUX_IN && active) {
+          mbar_expect_tx(&aux_full[grp], 128 * ROWB);
+          tma_load_2d(stg, &tmAuxIn, &aux_full[grp], gcol0, m0);
         }
       }
+      if (HAS_AUX_IN) {
+        if (active) {
+          mbar_wait(&aux_full[grp], aux_phase);
+          aux_phase ^= 1;
+        }
+      } else {
+        bar_sync(bar_id, 128);
+      }
+
+      // (2) accumulator -> registers -> staging
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      uint4 held[CG / 8];  // GELU with two outputs: activated values wait here while `pre` is stored
+      if (active) {
+#pragma unroll
+        for (int s = 0; s < CG / 32; ++s) {
+          const int col_in_tile = grp * CG + s * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + acc * BN + col_in_tile, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = n0 + col_in_tile + q * 8;
+            const bool col_ok = col < p.N;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+            if (OUT_F32) {
+              if (p.mask != nullptr && col_ok && row < p.M) {
+                const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + row * p.ldd + col);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (((mk.x >> (8 * j)) & 0xFF) == 0) v[j] = 0.f;
+                  if (((mk.y >> (8 * j)) & 0xFF) == 0) v[4 + j] = 0.f;
+                }
+              }
+              *reinterpret_cast<float4*>(stg + stg_off<ROWB>(r_tile, 2 * q)) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(stg + stg_off<ROWB>(r_tile, 2 * q + 1)) = make_float4(v[4], v[5], v[6], v[7]);
+              continue;
+            }
+            const int ch = s * 4 + q;  // 16-byte chunk of the staging row
+            uint8_t* slot = stg + stg_off<ROWB>(r_tile, ch);
+            if (EPI == MH_EPI_BF16 || EPI == MH_EPI_GELU || EPI == MH_EPI_RES) {
+              if (p.bias != nullptr && col_ok) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+            }
+            if (EPI == MH_EPI_GELU) {
+              // the reference evaluates GELU in fp32 on the half-precision fc1 output
+              // (fairseq_code/gelu.py:35 under autocast): round first, then activate.
+              const uint4 pre = f32_to_bf16x8(v);
+              if (p.has_aux_out) *reinterpret_cast<uint4*>(slot) = pre;
+              bf16x8_to_f32(pre, v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (EPI == MH_EPI_DGELU) {
+              float pre[8];
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), pre);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
+            }
+            if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
+              if (p.drop.thresh != 0)
+                drop_apply8(p.drop, static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + (col >> 3), v);
+            }
+            if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
+              float a[8];
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += a[j];
+            }
+            const uint4 o = f32_to_bf16x8(v);
+            if (EPI == MH_EPI_GELU && p.has_aux_out) held[ch] = o;
+            else *reinterpret_cast<uint4*>(slot) = o;
+          }
+        }
+      }
+      // (3) TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      // (4) staging -> global
+      if (active) {
+        fence_proxy_async_smem();
+        bar_sync(bar_id, 128);
+        if (EPI == MH_EPI_GELU && p.has_aux_out) {
+          if (leader) {
+            tma_store_2d(&tmAuxOut, stg, gcol0, m0);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          bar_sync(bar_id, 128);
+#pragma unroll
+          for (int ch = 0; ch < CG / 8; ++ch) *reinterpret_cast<uint4*>(stg + stg_off<ROWB>(r_tile, ch)) = held[ch];
+          fence_proxy_async_smem();
+          bar_sync(bar_id, 128);
+        }
+        if (leader) {
+          if (OUT_F32) tma_reduce_add_2d(&tmD, stg, gcol0, m0);
+          else tma_store_2d(&tmD, stg, gcol0, m0);
+          bulk_commit();
+        }
+      }
     }
+    if (leader) bulk_wait0();
   }
 
   tc_fence_before();
@@ -289,18 +355,19 @@ static EncodeTiledFn get_encode() {
 // 2-D bf16 row-major array [rows][cols] (leading dim ld elements), box = {box_cols, box_rows},
 // 128-byte swizzle, out-of-bounds reads return zeros.
 int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_cols,
-                 int box_rows) {
+                 int box_rows, int elem_bytes = 2, int swizzle_bytes = 128) {
   EncodeTiledFn enc = get_encode();
   MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
-  MH_CHECK(ld % 8 == 0, "TMA leading dimension must be a multiple of 8 elements (got %lld)", ld);
+  MH_CHECK((ld * elem_bytes) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld = %lld elements)", ld);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
            static_cast<int>(r), rows, cols, ld, box_cols, box_rows);
   return 0;
@@ -326,47 +393,54 @@ int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1,
 
 extern long long g_launches;
 
+struct GemmMaps {
+  CUtensorMap a, b, d, aux_in, aux_out;
+};
+
 template <int BN, int EPI, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid, cudaStream_t st) {
+static int launch(const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
   auto kfn = gemm_kernel<BN, EPI, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::kSmemBytes));
     configured = true;
   }
-  kfn<<<grid, GEMM_THREADS, TileCfg<BN>::kSmemBytes, st>>>(ta, tb, d);
+  kfn<<<grid, GEMM_THREADS, TileCfg<BN>::kSmemBytes, st>>>(t.a, t.b, t.d, t.aux_in, t.aux_out, d);
   MH_LAUNCH_CHECK();
   ++g_launches;
   return 0;
 }
 
 template <int BN, int EPI>
-static int dispatch_major(const mh_gemm_args* a, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d,
-                          int grid, cudaStream_t st) {
-  if (!a->a_mn && !a->b_mn) return launch<BN, EPI, false, false>(ta, tb, d, grid, st);
-  // dgrad reads the forward weight [N][K] as an MN-major B operand: plain / +add / dGELU outputs
-  if constexpr (EPI == MH_EPI_BF16 || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_F32) {
-    if (!a->a_mn && a->b_mn) return launch<BN, EPI, false, true>(ta, tb, d, grid, st);
+static int dispatch_major(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
+  if constexpr (EPI == MH_EPI_F32 && BN != 128) {
+    set_error("fp32 accumulate epilogue is built for block_n = 128 only");
+    return 1;
+  } else {
+    if (!a->a_mn && !a->b_mn) return launch<BN, EPI, false, false>(t, d, grid, st);
+    // dgrad reads the forward weight [N][K] as an MN-major B operand: plain / +add / dGELU outputs
+    if constexpr (EPI == MH_EPI_BF16 || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_F32) {
+      if (!a->a_mn && a->b_mn) return launch<BN, EPI, false, true>(t, d, grid, st);
+    }
+    // wgrad (dW = dY^T X) reads both activations MN-major
+    if constexpr (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
+      if (a->a_mn && a->b_mn) return launch<BN, EPI, true, true>(t, d, grid, st);
+      if (a->a_mn && !a->b_mn) return launch<BN, EPI, true, false>(t, d, grid, st);
+    }
+    set_error("operand layout a_mn=%d b_mn=%d is not built for epilogue %d", a->a_mn, a->b_mn, a->epilogue);
+    return 1;
   }
-  // wgrad (dW = dY^T X) reads both activations MN-major
-  if constexpr (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
-    if (a->a_mn && a->b_mn) return launch<BN, EPI, true, true>(ta, tb, d, grid, st);
-    if (a->a_mn && !a->b_mn) return launch<BN, EPI, true, false>(ta, tb, d, grid, st);
-  }
-  set_error("operand layout a_mn=%d b_mn=%d is not built for epilogue %d", a->a_mn, a->b_mn, a->epilogue);
-  return 1;
 }
 
 template <int BN>
-static int dispatch_epi(const mh_gemm_args* a, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, int grid,
-                        cudaStream_t st) {
+static int dispatch_epi(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
   switch (a->epilogue) {
-    case MH_EPI_BF16: return dispatch_major<BN, MH_EPI_BF16>(a, ta, tb, d, grid, st);
-    case MH_EPI_GELU: return dispatch_major<BN, MH_EPI_GELU>(a, ta, tb, d, grid, st);
-    case MH_EPI_RES: return dispatch_major<BN, MH_EPI_RES>(a, ta, tb, d, grid, st);
-    case MH_EPI_F32: return dispatch_major<BN, MH_EPI_F32>(a, ta, tb, d, grid, st);
-    case MH_EPI_DGELU: return dispatch_major<BN, MH_EPI_DGELU>(a, ta, tb, d, grid, st);
-    case MH_EPI_ADD: return dispatch_major<BN, MH_EPI_ADD>(a, ta, tb, d, grid, st);
+    case MH_EPI_BF16: return dispatch_major<BN, MH_EPI_BF16>(a, t, d, grid, st);
+    case MH_EPI_GELU: return dispatch_major<BN, MH_EPI_GELU>(a, t, d, grid, st);
+    case MH_EPI_RES: return dispatch_major<BN, MH_EPI_RES>(a, t, d, grid, st);
+    case MH_EPI_F32: return dispatch_major<BN, MH_EPI_F32>(a, t, d, grid, st);
+    case MH_EPI_DGELU: return dispatch_major<BN, MH_EPI_DGELU>(a, t, d, grid, st);
+    case MH_EPI_ADD: return dispatch_major<BN, MH_EPI_ADD>(a, t, d, grid, st);
   }
   set_error("unknown epilogue %d", a->epilogue);
   return 1;
@@ -386,14 +460,21 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   const int sms = sm_count();
+  const bool out_f32 = a->epilogue == MH_EPI_F32;
+  const int es = out_f32 ? 4 : 2;
+  MH_CHECK((a->ldd * es) % 16 == 0, "D row pitch must be a multiple of 16 bytes");
   const int num_m = (a->M + BM - 1) / BM;
   int bn = a->block_n;
+  if (out_f32) {
+    MH_CHECK(bn == 0 || bn == 128, "fp32 accumulate epilogue needs block_n = 128");
+    bn = 128;
+  }
   if (bn == 0) bn = (a->N >= 256 && num_m * ((a->N + 255) / 256) >= sms) ? 256 : 128;
   MH_CHECK(bn == 128 || bn == 256, "block_n must be 128 or 256");
   const int num_n = (a->N + bn - 1) / bn;
   const int kblocks = (a->K + BK - 1) / BK;
   int splits = 1;
-  if (a->epilogue == MH_EPI_F32) {
+  if (out_f32) {
     splits = a->split_k;
     if (splits <= 0) {
       splits = sms / (num_m * num_n);
@@ -407,27 +488,40 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
     splits = (kblocks + per - 1) / per;
   }
 
-  CUtensorMap ta, tb;
+  GemmMaps t;
   int rc;
-  if (!a->a_mn) rc = make_tmap_2d(&ta, a->A, a->M, a->K, a->lda, BK, BM);
-  else rc = make_tmap_2d(&ta, a->A, a->K, a->M, a->lda, 64, BK);
+  if (!a->a_mn) rc = make_tmap_2d(&t.a, a->A, a->M, a->K, a->lda, BK, BM);
+  else rc = make_tmap_2d(&t.a, a->A, a->K, a->M, a->lda, 64, BK);
   if (rc) return rc;
-  if (!a->b_mn) rc = make_tmap_2d(&tb, a->B, a->N, a->K, a->ldb, BK, bn);
-  else rc = make_tmap_2d(&tb, a->B, a->K, a->N, a->ldb, 64, BK);
+  if (!a->b_mn) rc = make_tmap_2d(&t.b, a->B, a->N, a->K, a->ldb, BK, bn);
+  else rc = make_tmap_2d(&t.b, a->B, a->K, a->N, a->ldb, 64, BK);
   if (rc) return rc;
+  // epilogue tiles: one box of 128 rows x (bn / 4) columns per column group
+  const int cg = bn / EPI_GROUPS;
+  const int rowb = cg * es;
+  rc = make_tmap_2d(&t.d, a->D, a->M, a->N, a->ldd, cg, BM, es, rowb);
+  if (rc) return rc;
+  t.aux_in = t.d;
+  t.aux_out = t.d;
+  if (a->aux_in != nullptr) {
+    rc = make_tmap_2d(&t.aux_in, a->aux_in, a->M, a->N, a->ld_aux, cg, BM, 2, rowb);
+    if (rc) return rc;
+  }
+  if (a->aux_out != nullptr) {
+    rc = make_tmap_2d(&t.aux_out, a->aux_out, a->M, a->N, a->ld_aux, cg, BM, 2, rowb);
+    if (rc) return rc;
+  }
 
   GemmDev d;
   d.M = a->M; d.N = a->N; d.K = a->K;
-  d.D = a->D; d.ldd = a->ldd;
+  d.ldd = a->ldd;
   d.bias = a->bias;
-  d.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
-  d.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
-  d.ld_aux = a->ld_aux;
+  d.has_aux_out = a->aux_out != nullptr;
   d.mask = a->mask;
   d.drop = make_drop(a->p_drop, a->seed, a->site);
   d.split_k = splits;
   const int tiles = num_m * num_n * splits;
   const int grid = tiles < sms ? tiles : sms;
-  if (bn == 256) return dispatch_epi<256>(a, ta, tb, d, grid, st);
-  return dispatch_epi<128>(a, ta, tb, d, grid, st);
+  if (bn == 256) return dispatch_epi<256>(a, t, d, grid, st);
+  return dispatch_epi<128>(a, t, d, grid, st);
 }

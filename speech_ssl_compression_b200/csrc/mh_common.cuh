@@ -29,7 +29,8 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 
-// ---- Philox4x32-10 ----
+// ---- Philox4x32-7 (Salmon et al., SC'11: 7 rounds is the smallest crush-resistant variant) ----
+// One 32x32->64 multiply per half round (IMAD.WIDE), round keys on the uniform datapath.
 struct Philox {
   uint32_t k0, k1;
   __device__ __forceinline__ Philox(uint64_t seed) : k0(static_cast<uint32_t>(seed)), k1(static_cast<uint32_t>(seed >> 32)) {}
@@ -37,11 +38,12 @@ struct Philox {
     uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = stream, c3 = 0x9E3779B9u;
     uint32_t a = k0, b = k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
-      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    for (int r = 0; r < 7; ++r) {
+      const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+      const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+      const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ a, n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ b;
+      c1 = static_cast<uint32_t>(p1); c3 = static_cast<uint32_t>(p0);
+      c0 = n0; c2 = n2;
       a += 0x9E3779B9u; b += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
@@ -65,6 +67,7 @@ __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
   d.offset = dropout_offset_ptr();
   d.site = site;
   d.thresh = p > 0.f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u;
+  if (d.thresh > 65535u) d.thresh = 65535u;
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   return d;
 }
@@ -84,12 +87,51 @@ __device__ __forceinline__ uint32_t drop_keep8(const DropCfg& d, uint64_t group)
   return m;
 }
 
+// the 128 random bits behind drop_keep8 (lane j of the group = 16-bit field j, low half first)
+__device__ __forceinline__ uint4 drop_bits8(const DropCfg& d, uint64_t group) {
+  const uint64_t seed = d.seed + (d.offset != nullptr ? 0x9E3779B97F4A7C15ull * __ldg(d.offset) : 0ull);
+  return Philox(seed)(group, d.site);
+}
+// v[j] = keep_j ? v[j] * scale : 0 for the 8 elements of `group`, without materialising the bit mask:
+// the high field is compared in place (word >= thresh << 16), the low one after a 16-bit shift.
+__device__ __forceinline__ void drop_apply8(const DropCfg& d, uint64_t group, float (&v)[8]) {
+  const uint4 r = drop_bits8(d, group);
+  const uint32_t t = d.thresh << 16;
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = (w[i] << 16) >= t ? v[2 * i] * d.scale : 0.f;
+    v[2 * i + 1] = w[i] >= t ? v[2 * i + 1] * d.scale : 0.f;
+  }
+}
+
 // ---- math ----
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU in fp32 (fairseq_code/gelu.py:34-35) without erff():
+//   erfc(a / sqrt 2) = 2^-g(a),  g(a) ~= a (c0 + c1 a + c2 a^2 + c3 a^3 + c4 a^4)  (least-squares fit on
+//   [0, 9], weighted by the sensitivity of gelu; |gelu error| < 7e-7 absolute over the whole line, i.e.
+//   below fp32 round-off of the reference's own erff for |x| > 1e-2 and 4 decimal orders below one bf16 ulp)
+//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2);   Phi(x) = x >= 0 ? 1 - e/2 : e/2.
+__device__ __forceinline__ float erfc_half_scaled(float a) {  // 0.5 * erfc(a / sqrt(2)), a >= 0
+  a = fminf(a, 12.f);
+  float p = 4.88221852e-04f;
+  p = fmaf(p, a, -7.19561887e-03f);
+  p = fmaf(p, a, 5.21302448e-02f);
+  p = fmaf(p, a, 4.59620056e-01f);
+  p = fmaf(p, a, 1.15099005e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-p * a - 1.0f));  // 2^(-g - 1)
+  return e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float a = fabsf(x);
+  return fmaf(-fminf(a, 12.f), erfc_half_scaled(a), fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float h = erfc_half_scaled(fabsf(x));
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  float pdf;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf) : "f"(-0.72134752044f * x * x));
+  return fmaf(x * 0.39894228040143268f, pdf, cdf);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -117,6 +117,9 @@ class MelHuBERTModel(nn.Module):
             sel = select.reshape(-1).to(torch.uint8)
             idx, count = K.select_rows(sel)
             n = B * T if self.static_rows else int(count.item())
+            if n == 0:  # e.g. the masked set of an un-masked forward: (0, K) logits like the reference
+                return (hidden.new_zeros((0, self.final_proj.out_features)),
+                        torch.empty(0, dtype=torch.int64, device=dev))
             rows = ops.GatherRows.apply(hidden, idx, n)
             logits = ops.linear(rows, self.final_proj)
             return logits, K.gather_labels(label_rows, idx, n)

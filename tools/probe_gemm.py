@@ -62,3 +62,36 @@ if which in ("all", "perf"):
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 20
             print(f"perf {nm:6s} M={M} N={N} K={Kd}: {ms*1e3:.1f} us  {2*M*N*Kd/ms/1e9:.1f} TFLOP/s", flush=True)
+
+if which in ("all", "epi"):
+    M = 24000
+    def timeit(fn, flops, name):
+        for _ in range(3): fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20): fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"epi {name:34s}: {ms*1e3:7.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+    x = torch.randn(M, 768, device=dev).to(torch.bfloat16)
+    w1 = torch.randn(3072, 768, device=dev).to(torch.bfloat16)
+    w2 = torch.randn(768, 3072, device=dev).to(torch.bfloat16)
+    wq = torch.randn(2304, 768, device=dev).to(torch.bfloat16)
+    b1 = torch.zeros(3072, device=dev); b2 = torch.zeros(768, device=dev); bq = torch.zeros(2304, device=dev)
+    u = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16); pre = torch.empty_like(u)
+    y = torch.empty(M, 768, device=dev, dtype=torch.bfloat16); res = torch.randn(M, 768, device=dev).to(torch.bfloat16)
+    qkv = torch.empty(M, 2304, device=dev, dtype=torch.bfloat16)
+    f1 = 2.0 * M * 3072 * 768
+    timeit(lambda: K.gemm(x, w1, u, epilogue=K.EPI_GELU, bias=b1, aux_out=pre, p_drop=0.1, seed=1, site=2), f1, "fc1 GELU+drop (2 outputs)")
+    timeit(lambda: K.gemm(x, w1, u, epilogue=K.EPI_GELU, bias=b1, aux_out=pre), f1, "fc1 GELU no drop")
+    timeit(lambda: K.gemm(x, w1, u, bias=b1), f1, "fc1 plain bias")
+    timeit(lambda: K.gemm(u, w2, y, epilogue=K.EPI_RES, bias=b2, aux_in=res, p_drop=0.1, seed=1, site=3), f1, "fc2 RES+drop")
+    timeit(lambda: K.gemm(u, w2, y, epilogue=K.EPI_RES, bias=b2, aux_in=res), f1, "fc2 RES no drop")
+    timeit(lambda: K.gemm(x, wq, qkv, bias=bq), 2.0 * M * 2304 * 768, "qkv plain bias")
+    timeit(lambda: K.gemm(y, w2, u, b_mn=True, epilogue=K.EPI_DGELU, aux_in=pre, p_drop=0.1, seed=1, site=2), f1, "fc2 dgrad DGELU+drop")
+    timeit(lambda: K.gemm(u, w1, y, b_mn=True, epilogue=K.EPI_ADD, aux_in=res), f1, "fc1 dgrad ADD")
+    g1 = torch.zeros(3072, 768, device=dev); g2 = torch.zeros(768, 3072, device=dev)
+    timeit(lambda: K.gemm(u, x, g1, a_mn=True, b_mn=True, epilogue=K.EPI_F32), f1, "fc1 wgrad f32")
+    timeit(lambda: K.gemm(y, u, g2, a_mn=True, b_mn=True, epilogue=K.EPI_F32), f1, "fc2 wgrad f32")
+    mk = torch.rand(3072, 768, device=dev) > 0.5
+    timeit(lambda: K.gemm(u, x, g1, a_mn=True, b_mn=True, epilogue=K.EPI_F32, mask=mk), f1, "fc1 wgrad f32 masked")

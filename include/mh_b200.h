@@ -108,6 +108,31 @@ int mh_dropout_apply(const void* x, void* y, int rows, int cols, float p_drop, u
 int mh_colsum(const void* x, long long ld, float* out, int rows, int cols, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Positional convolution (module.py:175-188 make pos_conv, :229-231 x = x + pos_conv(x)):
+ * weight-normed grouped Conv1d(C, C, k = 128, padding = 64, groups = C / 48) -> SamePad -> GELU,
+ * added to its input.  Implicit GEMM on tcgen05 with a sliding-window A operand (no im2col).
+ *   x, y, z, dz, dy, dx : bf16 [B*T, C] (frames x channels);  v : f32 [C, 48, 128], g : f32 [128]
+ *   w_fwd / w_bwd : bf16 [C/48][128][6][48][8] operand layouts written by mh_posconv_weight_prep
+ *   (w_bwd = taps flipped, in/out swapped, for the input gradient);  norm : f32 [128] = ||v[:, :, k]||
+ *   normsq_ws / dot_ws : f32 [128] scratch.
+ * forward : z = conv(x) + bias (saved),  y = x + gelu(z)
+ * backward: dz = dy * gelu'(z) (mh_gelu_bwd_mul);  dx = dy + conv^T(dz) (mh_posconv_dgrad);
+ *           dw[C,48,128] (f32) += dz^T * window(x) (mh_posconv_wgrad);  dv += ..., dg += ... through the
+ *           weight norm (mh_posconv_weight_bwd);  the bias gradient is mh_colsum(dz).
+ * ------------------------------------------------------------------------------------- */
+int mh_posconv_weight_prep(const float* v, const float* g, void* w_fwd, void* w_bwd, float* normsq_ws, float* norm,
+                           int C, int groups, int ktaps, void* stream);
+int mh_posconv_fwd(const void* x, const void* w_fwd, const float* bias, void* z, void* y, int B, int T, int C,
+                   int groups, int ktaps, void* stream);
+int mh_posconv_dgrad(const void* dz, const void* w_bwd, const void* dy, void* dx, int B, int T, int C, int groups,
+                     int ktaps, void* stream);
+int mh_gelu_bwd_mul(const void* dy, const void* z, void* dz, long long n, void* stream);
+int mh_posconv_wgrad(const void* dz, const void* x, float* dw, int B, int T, int C, int groups, int ktaps,
+                     void* stream);
+int mh_posconv_weight_bwd(const float* dw, const float* v, const float* g, const float* norm, float* dot_ws, float* dv,
+                          float* dg, int C, int groups, int ktaps, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Weight preparation W0: fp32 master (+ optional bool mask) -> bf16 operand, optionally also
  * its transpose (for dgrad).  Replaces the per-forward prune hook
  * pytorch_code/prune.py:24-38,64-85 (weight_orig.masked_fill(~mask, 0)) x 144 tensors and the

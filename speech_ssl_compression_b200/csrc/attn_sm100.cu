@@ -125,7 +125,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
           umma_bf16(tmem_o, make_sdesc(ap + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
-                    make_sdesc(bv + k * 2048, TILE_BYTES, 1024), idesc_o, k > 0);
+                    make_sdesc(bv + k * 2048, TILE_BYTES, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(o_full);
         if (j + 1 < n_kv) issue_s(j + 1);
@@ -134,14 +134,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ softmax warps
+    // Thread t owns query row t.  O accumulates in TMEM across key blocks; the running maximum is only
+    // raised when a block exceeds it by more than 2^8 (lazy rescaling: probabilities stay <= 256, the
+    // final division by the row sum is exact either way), so the O read-modify-write is a rare path.
     const int r = threadIdx.x;  // query row inside the tile == TMEM lane
     const int q = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const uint64_t row_id = (static_cast<uint64_t>(b) * p.H + h) * p.T + q;
     const uint64_t groups_per_row = (p.T + 7) >> 3;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int k0 = j * BKV;
@@ -149,77 +150,125 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tc_fence_after();
       int lim = kv_len - k0;                       // keys [0, lim) of this block are visible
       if (p.causal) lim = min(lim, q - k0 + 1);
-      // pass 1: row maximum
+      const bool full = __all_sync(0xffffffffu, lim >= BKV);
+      // ---- pass 1: row maximum (TMEM loads double buffered against the max reduction)
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_s + lane_off + c * 32, rr);
-        tmem_ld_wait();
+      {
+        uint32_t ra[32], rb[32];
+        auto red = [&](const uint32_t (&rr)[32], int c) {
+          if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < lim) mx = fmaxf(mx, __uint_as_float(rr[i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < lim) mx = fmaxf(mx, __uint_as_float(rr[i]));
+          }
+        };
+        tmem_ld32(tmem_s + lane_off, ra);
+        tmem_ld_wait();
+        tmem_ld32(tmem_s + lane_off + 32, rb);
+        red(ra, 0);
+        tmem_ld_wait();
+        tmem_ld32(tmem_s + lane_off + 64, ra);
+        red(rb, 1);
+        tmem_ld_wait();
+        tmem_ld32(tmem_s + lane_off + 96, rb);
+        red(ra, 2);
+        tmem_ld_wait();
+        red(rb, 3);
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float m_use = m_new == -INFINITY ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);  // m_run = -inf -> 0
-      // pass 2: probabilities, row sum, dropout, bf16 P into swizzled smem
-      float l_blk = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_s + lane_off + c * 32, rr);
-        tmem_ld_wait();
+      const float m_blk = mx * sc;
+      if (j == 0) {
+        m_run = m_blk;
+      } else {
+        const bool need = m_blk > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // rescale this warp's rows of O (PV_{j-1} must have landed first)
+          const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t rr[32];
+            tmem_ld32(tmem_o + lane_off + c * 32, rr);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int kk = c * 32 + g * 8 + i;
-            const float e = exp2f(__uint_as_float(rr[g * 8 + i]) * p.scale_log2 - m_use);
-            pv[i] = kk < lim ? e : 0.f;
-            l_blk += pv[i];
+            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * alpha);
+            tmem_st32(tmem_o + lane_off + c * 32, rr);
           }
-          if (p.drop.thresh != 0) {
-            const uint32_t keep = drop_keep8(p.drop, row_id * groups_per_row + ((k0 + c * 32 + g * 8) >> 3));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = ((keep >> i) & 1) ? pv[i] * p.drop.scale : 0.f;
-          }
-          const int kc = c * 32 + g * 8;  // key column inside the block
-          uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
-          *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
+          tmem_st_wait();
+          l_run *= alpha;
+          if (need) m_run = m_blk;
         }
       }
-      l_run = l_run * alpha + l_blk;
-      m_run = m_new;
+      const float m_use = m_run == -INFINITY ? 0.f : m_run;
+      // ---- pass 2: probabilities, row sum, dropout, bf16 P into swizzled smem
+      float l_blk = 0.f;
+      {
+        uint32_t ra[32], rb[32];
+        auto emit = [&](const uint32_t (&rr)[32], int c) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float e = ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_use));
+              pv[i] = (full || c * 32 + g * 8 + i < lim) ? e : 0.f;
+              l_blk += pv[i];
+            }
+            if (p.drop.thresh != 0) drop_apply8(p.drop, row_id * groups_per_row + ((k0 + c * 32 + g * 8) >> 3), pv);
+            const int kc = c * 32 + g * 8;  // key column inside the block
+            uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
+            *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
+          }
+        };
+        tmem_ld32(tmem_s + lane_off, ra);
+        tmem_ld_wait();
+        tmem_ld32(tmem_s + lane_off + 32, rb);
+        emit(ra, 0);
+        tmem_ld_wait();
+        tmem_ld32(tmem_s + lane_off + 64, ra);
+        emit(rb, 1);
+        tmem_ld_wait();
+        tmem_ld32(tmem_s + lane_off + 96, rb);
+        emit(ra, 2);
+        tmem_ld_wait();
+        emit(rb, 3);
+      }
+      l_run += l_blk;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
-      // O += P V
-      mbar_wait(o_full, j & 1);
+    }
+    if (n_kv > 0) {
+      mbar_wait(o_full, (n_kv - 1) & 1);
       tc_fence_after();
+    }
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + q) * p.E + h * HD;
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t rr[32];
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t rr[32];
+      if (n_kv > 0) {
         tmem_ld32(tmem_o + lane_off + c * 32, rr);
         tmem_ld_wait();
+      } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(rr[i]);
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
       }
-      tc_fence_before();
-    }
-    if (q < p.T) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + q) * p.E + h * HD;
+      if (q < p.T) {
 #pragma unroll
-      for (int g = 0; g < HD / 8; ++g) {
-        float v[8];
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = o[g * 8 + i] * inv;
-        stg128(dst + g * 8, f32_to_bf16x8(v));
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[g * 8 + i]) * inv;
+          stg128(dst + c * 32 + g * 8, f32_to_bf16x8(v));
+        }
       }
-      p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
     }
+    if (q < p.T) p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
@@ -262,7 +311,7 @@ struct AttnBwdParams {
 
 // smem: K, V (16 KB each) | Q[2], dO[2] (64 KB) | P (32 KB) | dS (32 KB)
 constexpr int BWD_SMEM = TILE_BYTES * (2 + 4 + 2 + 2) + 1024 + 256;
-constexpr int BWD_THREADS = 320;  // warps 0-7 compute, 8 = TMA, 9 = MMA
+constexpr int BWD_THREADS = 576;  // warps 0-15 compute, 16 = TMA, 17 = MMA
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
@@ -293,18 +342,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const int i_begin = p.causal ? k0 / BQ : 0;  // query blocks that can see this key block
   const bool active = k0 < kv_len;             // a fully padded key block has zero gradient
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, 512);
     mbar_init(dq_full, 1);
     mbar_init(fin_full, 1);
     fence_mbar_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 17) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -313,7 +362,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                  tm_dq = tmem_base + 384;
 
   if (active) {
-    if (warp == 8) {
+    if (warp == 16) {
       if (elect_one()) {
         mbar_expect_tx(kv_full, 2 * TILE_BYTES);
         tma_load_3d(sK, &tm_qkv, kv_full, p.E + h * HD, k0, b);
@@ -327,7 +376,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }
       __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 17) {
       if (elect_one()) {
         const uint32_t id_s = make_idesc_bf16(BQ, BKV, false, false);   // S, dP: [q x k], both K-major
         const uint32_t id_kv = make_idesc_bf16(BKV, HD, true, true);    // dV, dK: [k x hd], A and B MN-major
@@ -380,64 +429,74 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       __syncwarp();
     } else {
       // ---------------------------------------------------------------- compute warps
-      const int quad = warp & 3, half = warp >> 2;
-      const int r = quad * 32 + lane;  // query row inside the tile (S / dP / dQ) or key row (dK / dV)
+      // thread = (row r of the tile, 32-column part): S / dP / dQ rows are queries, dK / dV rows are keys
+      const int quad = warp & 3, part = warp >> 2;
+      const int r = quad * 32 + lane;
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
       const uint64_t groups_per_row = (p.T + 7) >> 3;
       const int n_iter = n_q - i_begin;
+      const int kc0 = part * 32;
+      const uint32_t thr = p.drop.thresh << 16;
+      const float zs = p.drop.scale * p.scale;
       for (int n = 0; n < n_iter; ++n) {
         const int i = i_begin + n;
         const int q = i * BQ + r;
         const bool q_ok = q < p.T;
         const long long sidx = (static_cast<long long>(b) * p.H + h) * p.T + q;
-        const float lse = q_ok ? p.lse[sidx] : INFINITY;
-        const float dl = q_ok ? p.delta[sidx] : 0.f;
+        const float lse = q_ok ? p.lse[sidx] : INFINITY;  // +inf -> P = 0 for rows past the sequence end
+        const float dls = q_ok ? p.delta[sidx] * p.scale : 0.f;
         const uint64_t row_id = static_cast<uint64_t>(sidx);
         int lim = kv_len - k0;
         if (p.causal) lim = min(lim, q - k0 + 1);
+        const bool full = __all_sync(0xffffffffu, lim >= BKV);
         mbar_wait(sdp_full, n & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {  // this warp's 64 key columns in two chunks of 32
-          const int kc0 = half * 64 + c * 32;
-          uint32_t rs[32], rd[32];
-          tmem_ld32(tm_s + lane_off + kc0, rs);
-          tmem_ld32(tm_dp + lane_off + kc0, rd);
-          tmem_ld_wait();
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tm_s + lane_off + kc0, rs);
+        tmem_ld32(tm_dp + lane_off + kc0, rd);
+        tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float pd[8], ds[8];
-            uint32_t keep = 0xFFu;
-            if (p.drop.thresh != 0) keep = drop_keep8(p.drop, row_id * groups_per_row + ((k0 + kc0 + g * 8) >> 3));
+        for (int g = 0; g < 4; ++g) {
+          float pd[8], ds[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            float pr = ex2_approx(fmaf(__uint_as_float(rs[g * 8 + t]), p.scale_log2, -lse));
+            if (!full) pr = (kc0 + g * 8 + t < lim) ? pr : 0.f;
+            pd[t] = pr;
+          }
+          if (p.drop.thresh != 0) {
+            const uint4 bits = drop_bits8(p.drop, row_id * groups_per_row + ((k0 + kc0 + g * 8) >> 3));
+            const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              const int kk = kc0 + g * 8 + t;
-              float pr = exp2f(__uint_as_float(rs[g * 8 + t]) * p.scale_log2 - lse);
-              pr = (kk < lim && q_ok) ? pr : 0.f;
-              const float z = ((keep >> t) & 1) ? p.drop.scale : 0.f;
-              pd[t] = pr * z;
-              ds[t] = pr * (__uint_as_float(rd[g * 8 + t]) * z - dl) * p.scale;
+              const bool keep = ((t & 1) ? w[t >> 1] : (w[t >> 1] << 16)) >= thr;
+              const float pr = pd[t];
+              ds[t] = pr * fmaf(__uint_as_float(rd[g * 8 + t]), keep ? zs : 0.f, -dls);
+              pd[t] = keep ? pr * p.drop.scale : 0.f;
             }
-            const int kc = kc0 + g * 8;
-            const uint32_t off = (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
-            *reinterpret_cast<uint4*>(sP + off) = f32_to_bf16x8(pd);
-            *reinterpret_cast<uint4*>(sdS + off) = f32_to_bf16x8(ds);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) ds[t] = pd[t] * fmaf(__uint_as_float(rd[g * 8 + t]), p.scale, -dls);
           }
+          const int kc = kc0 + g * 8;
+          const uint32_t off = (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
+          *reinterpret_cast<uint4*>(sP + off) = f32_to_bf16x8(pd);
+          *reinterpret_cast<uint4*>(sdS + off) = f32_to_bf16x8(ds);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(pds_full);
-        // dQ_i: this warp's 32 of the 64 head-dim columns
+        // dQ_i: this warp's 16 of the 64 head-dim columns
         mbar_wait(dq_full, n & 1);
         tc_fence_after();
         {
-          uint32_t rq[32];
-          tmem_ld32(tm_dq + lane_off + half * 32, rq);
+          uint32_t rq[16];
+          tmem_ld16(tm_dq + lane_off + part * 16, rq);
           tmem_ld_wait();
           if (q_ok) {
-            float* dst = p.dq_acc + (static_cast<long long>(b) * p.T + q) * p.E + h * HD + half * 32;
+            float* dst = p.dq_acc + (static_cast<long long>(b) * p.T + q) * p.E + h * HD + part * 16;
 #pragma unroll
-            for (int t = 0; t < 32; t += 4)
+            for (int t = 0; t < 16; t += 4)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + t), "f"(__uint_as_float(rq[t])),
                            "f"(__uint_as_float(rq[t + 1])), "f"(__uint_as_float(rq[t + 2])),
                            "f"(__uint_as_float(rq[t + 3]))
@@ -446,18 +505,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
         tc_fence_before();
       }
-      // final dK / dV: row r = key k0 + r
+      // final dK / dV: row r = key k0 + r, this warp's 16 head-dim columns
       mbar_wait(fin_full, 0);
       tc_fence_after();
       const int key = k0 + r;
-      uint32_t rk[32], rv[32];
-      tmem_ld32(tm_dk + lane_off + half * 32, rk);
-      tmem_ld32(tm_dv + lane_off + half * 32, rv);
+      uint32_t rk[16], rv[16];
+      tmem_ld16(tm_dk + lane_off + part * 16, rk);
+      tmem_ld16(tm_dv + lane_off + part * 16, rv);
       tmem_ld_wait();
       if (key < p.T) {
-        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + half * 32;
+        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + part * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           float a[8], c[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
@@ -469,14 +528,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 16) {
     // fully padded key block: dK = dV = 0
-    const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int r = (warp & 3) * 32 + lane, part = warp >> 2;
     const int key = k0 + r;
     if (key < p.T) {
-      __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + half * 32;
+      __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + part * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
         stg128(base + p.E + g * 8, make_uint4(0, 0, 0, 0));
         stg128(base + 2 * p.E + g * 8, make_uint4(0, 0, 0, 0));
       }
@@ -484,7 +543,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == 17) tmem_dealloc(tmem_base, 512);
 }
 
 // dqkv[:, 0:E] = bf16(dq_acc)

@@ -340,7 +340,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* ptr = nullptr;
@@ -356,7 +356,7 @@ static EncodeTiledFn get_encode() {
 // 128-byte swizzle, out-of-bounds reads return zeros.
 int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_cols,
                  int box_rows, int elem_bytes = 2, int swizzle_bytes = 128) {
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = get_encode_tiled();
   MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
   MH_CHECK((ld * elem_bytes) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld = %lld elements)", ld);
@@ -376,7 +376,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
 // 3-D variant used by attention: [d2][d1][d0] with strides in elements.
 int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
                  long long stride2, int box0, int box1) {
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = get_encode_tiled();
   MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
   MH_CHECK(stride1 % 8 == 0 && stride2 % 8 == 0, "TMA strides must be multiples of 8 elements");

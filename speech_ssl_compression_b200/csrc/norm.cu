@@ -65,9 +65,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
         if (drop.thresh != 0) {
-          const uint32_t keep = drop_keep8(drop, static_cast<uint64_t>(row) * nchunks + c);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1) ? o[j] * drop.scale : 0.f;
+          drop_apply8(drop, static_cast<uint64_t>(row) * nchunks + c, o);
         }
         stg128(yr + c * 8, f32_to_bf16x8(o));
       }
@@ -110,9 +108,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         bf16x8_to_f32(ldg128(dy + off + c * 8), d);
         bf16x8_to_f32(ldg128(x + off + c * 8), xv);
         if (din.thresh != 0) {
-          const uint32_t keep = drop_keep8(din, static_cast<uint64_t>(row) * nchunks + c);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] = ((keep >> j) & 1) ? d[j] * din.scale : 0.f;
+          drop_apply8(din, static_cast<uint64_t>(row) * nchunks + c, d);
         }
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
@@ -140,9 +136,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         stg128(dx + off + c * 8, f32_to_bf16x8(o));
         if (dx_drop != nullptr) {
           if (dout.thresh != 0) {
-            const uint32_t keep = drop_keep8(dout, static_cast<uint64_t>(row) * nchunks + c);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1) ? o[j] * dout.scale : 0.f;
+            drop_apply8(dout, static_cast<uint64_t>(row) * nchunks + c, o);
           }
           stg128(dx_drop + off + c * 8, f32_to_bf16x8(o));
         }

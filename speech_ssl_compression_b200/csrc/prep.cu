@@ -197,9 +197,7 @@ __global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v[8];
     bf16x8_to_f32(ldg128(x + i * 8), v);
-    const uint32_t keep = drop_keep8(drop, static_cast<uint64_t>(i));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1) ? v[j] * drop.scale : 0.f;
+    drop_apply8(drop, static_cast<uint64_t>(i), v);
     stg128(y + i * 8, f32_to_bf16x8(v));
   }
 }

@@ -143,6 +143,57 @@ def colsum_add(x, out):
     _call("mh_colsum", _p(x), c_longlong(x.stride(0)), _p(out), c_int(x.shape[0]), c_int(x.shape[1]), _s())
 
 
+# ------------------------------------------------------------------------------ positional conv
+def posconv_weight_prep(v, g, want_bwd=True):
+    """v f32 [C, 48, 128], g f32 [..., 128] -> (w_fwd, w_bwd or None, norm[128]) operand tensors."""
+    C, cg, taps = v.shape
+    dev = v.device
+    w_fwd = torch.empty(C * cg * taps, device=dev, dtype=bf16)
+    w_bwd = torch.empty(C * cg * taps, device=dev, dtype=bf16) if want_bwd else None
+    ws = torch.empty(taps, device=dev, dtype=torch.float32)
+    norm = torch.empty(taps, device=dev, dtype=torch.float32)
+    _call("mh_posconv_weight_prep", _p(v), _p(g), _p(w_fwd), _p(w_bwd), _p(ws), _p(norm), c_int(C), c_int(C // cg),
+          c_int(taps), _s())
+    return w_fwd, w_bwd, norm
+
+
+def posconv_fwd(x, w_fwd, bias, B, T, groups=16, taps=128, want_z=True):
+    """x bf16 [B*T, C] -> (y = x + gelu(conv(x) + bias), z = conv(x) + bias or None)"""
+    C = x.shape[1]
+    y = torch.empty_like(x)
+    z = torch.empty_like(x) if want_z else None
+    _call("mh_posconv_fwd", _p(x), _p(w_fwd), _p(bias), _p(z), _p(y), c_int(B), c_int(T), c_int(C), c_int(groups),
+          c_int(taps), _s())
+    return y, z
+
+
+def posconv_dgrad(dz, w_bwd, dy, B, T, groups=16, taps=128):
+    """dx = dy + conv^T(dz)"""
+    dx = torch.empty_like(dz)
+    _call("mh_posconv_dgrad", _p(dz), _p(w_bwd), _p(dy), _p(dx), c_int(B), c_int(T), c_int(dz.shape[1]), c_int(groups),
+          c_int(taps), _s())
+    return dx
+
+
+def gelu_bwd_mul(dy, z):
+    dz = torch.empty_like(dy)
+    _call("mh_gelu_bwd_mul", _p(dy), _p(z), _p(dz), c_longlong(dy.numel()), _s())
+    return dz
+
+
+def posconv_wgrad(dz, x, dw, B, T, groups=16, taps=128):
+    """dw f32 [C, 48, 128] += correlation of dz with the input window"""
+    _call("mh_posconv_wgrad", _p(dz), _p(x), _p(dw), c_int(B), c_int(T), c_int(x.shape[1]), c_int(groups), c_int(taps),
+          _s())
+
+
+def posconv_weight_bwd(dw, v, g, norm, dv, dg):
+    C, cg, taps = v.shape
+    ws = torch.empty(taps, device=v.device, dtype=torch.float32)
+    _call("mh_posconv_weight_bwd", _p(dw), _p(v), _p(g), _p(norm), _p(ws), _p(dv), _p(dg), c_int(C), c_int(C // cg),
+          c_int(taps), _s())
+
+
 # ------------------------------------------------------------------------------ prep / movement
 def weight_prep(src, mask, dst, dst_t=None):
     """src fp32 [rows, cols] (contiguous), mask bool/u8 or None; dst bf16 view [rows, cols] (any ld);

@@ -109,9 +109,10 @@ class TransformerEncoder(nn.Module):
         C = x.shape[1]
         if pad_rows is not None:
             x = ops.ZeroRows.apply(x, pad_rows)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            pos = self.pos_conv(x.view(B, T, C).transpose(1, 2)).transpose(1, 2)
-        x = x + pos.reshape(B * T, C)
+        if not ops.posconv_supported(self.pos_conv[0]):
+            raise NotImplementedError("the positional-conv kernels are built for Conv1d(k=128, pad=64, 48 channels per "
+                                      "group, weight-normed) -- the shape of every MelHuBERT config")
+        x = ops.pos_conv(x, self.pos_conv[0], B, T)  # x + gelu(same_pad(conv_wn(x)))
         p = self.dropout if self.training else 0.0
         if not self.layer_norm_first:
             x = ops.layer_norm(x, self.layer_norm, p, seed, SITE_ENCODER_DROPOUT)

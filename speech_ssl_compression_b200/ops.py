@@ -152,6 +152,63 @@ def layer_norm(x, ln, p_drop=0.0, seed=0, site=0):
 
 
 # ---------------------------------------------------------------------------------------------
+# positional convolution (module.py:175-188, 229-231): x + GELU(SamePad(Conv1d_wn(x)))
+# ---------------------------------------------------------------------------------------------
+def posconv_supported(conv):
+    return (isinstance(conv, torch.nn.Conv1d) and conv.kernel_size == (128,) and conv.padding == (64,)
+            and conv.in_channels == conv.out_channels and conv.in_channels // conv.groups == 48
+            and hasattr(conv, "weight_v") and hasattr(conv, "weight_g"))
+
+
+def _posconv_operands(conv):
+    v, g = conv.weight_v, conv.weight_g
+    trainable = v.requires_grad or g.requires_grad
+    sig = (_EPOCH[0] if trainable else -1, _sig([v, g]))
+    hit = conv.__dict__.get("_mh_posconv")
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    with torch.no_grad():
+        ops_ = K.posconv_weight_prep(v.detach(), g.detach().reshape(-1))
+    conv.__dict__["_mh_posconv"] = (sig, ops_)
+    return ops_
+
+
+class PosConvFn(torch.autograd.Function):
+    """rows [B*T, C] bf16 -> rows + gelu(conv(rows) + bias); implicit-GEMM tcgen05 kernels fwd / dgrad / wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, conv, B, T, *params):
+        w_fwd, w_bwd, norm = _posconv_operands(conv)
+        need = any(ctx.needs_input_grad)
+        y, z = K.posconv_fwd(x, w_fwd, conv.bias.detach(), B, T, conv.groups, 128, want_z=need)
+        if need:
+            ctx.conv, ctx.dims = conv, (B, T)
+            ctx.save_for_backward(x, z, w_bwd, norm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z, w_bwd, norm = ctx.saved_tensors
+        conv = ctx.conv
+        B, T = ctx.dims
+        dy = dy.contiguous()
+        dz = K.gelu_bwd_mul(dy, z)
+        dx = K.posconv_dgrad(dz, w_bwd, dy, B, T, conv.groups, 128) if ctx.needs_input_grad[0] else None
+        v, g = conv.weight_v, conv.weight_g
+        if v.requires_grad or g.requires_grad:
+            dw = torch.zeros(v.shape, device=v.device, dtype=torch.float32)
+            K.posconv_wgrad(dz, x, dw, B, T, conv.groups, 128)
+            K.posconv_weight_bwd(dw, v.detach(), g.detach().reshape(-1), norm, _grad_of(v), _grad_of(g).view(-1))
+        if conv.bias is not None and conv.bias.requires_grad:
+            K.colsum_add(dz, _grad_of(conv.bias))
+        return (dx,) + (None,) * (len(ctx.needs_input_grad) - 1)
+
+
+def pos_conv(x, conv, B, T):
+    return PosConvFn.apply(x, conv, B, T, *[p for p in conv.parameters()])
+
+
+# ---------------------------------------------------------------------------------------------
 # fused transformer encoder layer (module.py:82-133 + multihead_attention.py:98-172 +
 # forward_multihead_attention.py:39-243)
 # ---------------------------------------------------------------------------------------------

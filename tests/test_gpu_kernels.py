@@ -470,3 +470,39 @@ def test_fused_adam_matches_torch_adam_with_clipping():
         assert grad.abs().max().item() == 0
         assert rel(p, ref_p) < 1e-6
     assert (p - ref_p).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------------------- positional conv
+@pytest.mark.parametrize("B,T", [(1, 128), (2, 300), (4, 750), (2, 791), (1, 1500)])
+def test_positional_conv_fwd_bwd_vs_torch(B, T):
+    """module.py:175-188,229-231: x + GELU(SamePad(weight-normed grouped Conv1d(x))) and its three gradients."""
+    F = torch.nn.functional
+    k = K()
+    C, groups, taps = 768, 16, 128
+    v = torch.randn(C, C // groups, taps, device=DEV) * 0.02
+    g = torch.rand(1, 1, taps, device=DEV) + 0.5
+    bias = torch.randn(C, device=DEV) * 0.1
+    x = torch.randn(B * T, C, device=DEV).to(bf16)
+    w_fwd, w_bwd, norm = k.posconv_weight_prep(v, g.reshape(-1))
+    y, z = k.posconv_fwd(x, w_fwd, bias, B, T)
+    vr, gr = v.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    w = torch._weight_norm(vr, gr, 2)
+    xr = x.float().view(B, T, C).requires_grad_(True)
+    zr = F.conv1d(xr.transpose(1, 2), w, bias, padding=taps // 2, groups=groups)[:, :, :-1].transpose(1, 2)
+    yr = xr + F.gelu(zr)
+    assert rel(z, zr.reshape(B * T, C)) < 4e-3 and rel(y, yr.reshape(B * T, C)) < 4e-3
+    dy = torch.randn(B * T, C, device=DEV).to(bf16)
+    yr.backward(dy.float().view(B, T, C))
+    dz = k.gelu_bwd_mul(dy, z)
+    dx = k.posconv_dgrad(dz, w_bwd, dy, B, T)
+    assert rel(dx, xr.grad.reshape(B * T, C)) < 5e-3
+    dw = torch.zeros(C, C // groups, taps, device=DEV)
+    k.posconv_wgrad(dz, x, dw, B, T)
+    dv, dg = torch.zeros_like(v), torch.zeros(taps, device=DEV)
+    k.posconv_weight_bwd(dw, v, g.reshape(-1), norm, dv, dg)
+    assert rel(dv, vr.grad) < 6e-3 and rel(dg, gr.grad.reshape(-1)) < 6e-3
+    db = torch.zeros(C, device=DEV)
+    k.colsum_add(dz, db)
+    zr2 = zr.detach().requires_grad_(True)
+    F.gelu(zr2).backward(dy.float().view(B, T, C))
+    assert rel(db, zr2.grad.sum((0, 1))) < 6e-3

@@ -23,7 +23,7 @@
 namespace mh {
 extern long long g_launches;
 int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
-                 long long stride2, int box0, int box1);
+                 long long stride2, int box0, int box1, int elem_bytes = 2);
 
 constexpr int HD = 64;
 constexpr int BQ = 128;
@@ -143,6 +143,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     const uint64_t row_id = (static_cast<uint64_t>(b) * p.H + h) * p.T + q;
     const uint64_t groups_per_row = (p.T + 7) >> 3;
     const float sc = p.scale_log2;
+    const bool use_drop = p.drop.thresh != 0;
+    const DropState ds(p.drop);
+    // the dropout keep-scale 1/(1-p) is folded into the exponent: probabilities (and the running row sum)
+    // carry the constant factor, which the final normalisation and the saved log-sum-exp divide out again
+    const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int k0 = j * BKV;
@@ -202,7 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
           if (need) m_run = m_blk;
         }
       }
-      const float m_use = m_run == -INFINITY ? 0.f : m_run;
+      const float m_off = (m_run == -INFINITY ? 0.f : m_run) - lg_scale;
       // ---- pass 2: probabilities, row sum, dropout, bf16 P into swizzled smem
       float l_blk = 0.f;
       {
@@ -211,13 +216,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float pv[8];
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float e = ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_use));
-              pv[i] = (full || c * 32 + g * 8 + i < lim) ? e : 0.f;
-              l_blk += pv[i];
+              for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_off));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                pv[i] = (c * 32 + g * 8 + i < lim) ? ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_off)) : 0.f;
             }
-            if (p.drop.thresh != 0) drop_apply8(p.drop, row_id * groups_per_row + ((k0 + c * 32 + g * 8) >> 3), pv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) l_blk += pv[i];
+            if (use_drop) {
+              const uint4 bits = ds.bits(row_id * groups_per_row + ((k0 + c * 32 + g * 8) >> 3));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pv[i] = ds.keep(bits, i) ? pv[i] : 0.f;
+            }
             const int kc = c * 32 + g * 8;  // key column inside the block
             uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
             *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
@@ -245,7 +258,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       mbar_wait(o_full, (n_kv - 1) & 1);
       tc_fence_after();
     }
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    // with the keep-scale s folded in: l_run = s * sum(e), O_tmem = s * sum(keep e v)  ->  out = O_tmem * s / l_run
+    const float inv = l_run > 0.f ? (use_drop ? p.drop.scale : 1.f) / l_run : 0.f;
     __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + q) * p.E + h * HD;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
@@ -267,7 +281,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         }
       }
     }
-    if (q < p.T) p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
+    if (q < p.T)
+      p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) - lg_scale : INFINITY;
     tc_fence_before();
   }
   tc_fence_before();
@@ -276,24 +291,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 }
 
 // ----------------------------------------------------------------------------- backward
-// delta[b,h,q] = sum_d dO[row, h*64+d] * O[row, h*64+d]; one warp per (row, head).
+// delta[b,h,q] = sum_d dO[row, h*64+d] * O[row, h*64+d]: 8 lanes x 16 bytes per (row, head), coalesced.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                   int B, int T, int H) {
-  const int lane = threadIdx.x & 31;
-  const long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);  // (row, head) pair
-  const long long total = static_cast<long long>(B) * T * H;
-  if (w >= total) return;
-  const long long row = w / H;
-  const int h = static_cast<int>(w % H);
-  const long long off = row * (static_cast<long long>(H) * HD) + h * HD + lane * 2;
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + off);
-  const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(d_o + off);
-  float s = __bfloat162float(a.x) * __bfloat162float(g.x) + __bfloat162float(a.y) * __bfloat162float(g.y);
-  s = warp_sum(s);
-  if (lane == 0) {
-    const long long bb = row / T, t = row % T;
-    delta[(bb * H + h) * T + t] = s;
+  const long long total = static_cast<long long>(B) * T * H * 8;  // 16-byte chunks
+  for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < ((total + 31) & ~31LL);
+       c += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    if (c < total) {
+      float a[8], g[8];
+      bf16x8_to_f32(ldg128(o + c * 8), a);
+      bf16x8_to_f32(ldg128(d_o + c * 8), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(a[j], g[j], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((threadIdx.x & 7) == 0 && c < total) {
+      const long long pair = c >> 3;  // (row, head)
+      const long long row = pair / H;
+      const int h = static_cast<int>(pair % H);
+      const long long bb = row / T, t = row % T;
+      delta[(bb * H + h) * T + t] = s;
+    }
   }
 }
 
@@ -309,13 +331,14 @@ struct AttnBwdParams {
   DropCfg drop;
 };
 
-// smem: K, V (16 KB each) | Q[2], dO[2] (64 KB) | P (32 KB) | dS (32 KB)
-constexpr int BWD_SMEM = TILE_BYTES * (2 + 4 + 2 + 2) + 1024 + 256;
+// smem: K, V (16 KB each) | Q[2], dO[2] (64 KB) | P (32 KB) | dS (32 KB) | dQ staging 2 x [128 x 64] f32 (64 KB)
+constexpr int BWD_DQ_STAGE = 128 * 64 * 4;
+constexpr int BWD_SMEM = TILE_BYTES * (2 + 4 + 2 + 2) + 2 * BWD_DQ_STAGE + 1024 + 256;
 constexpr int BWD_THREADS = 576;  // warps 0-15 compute, 16 = TMA, 17 = MMA
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -324,7 +347,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sdO = sQ + 2 * TILE_BYTES;   // 2 stages
   uint8_t* sP = sdO + 2 * TILE_BYTES;   // [128 q rows][128 keys] as 2 atoms of 64 keys
   uint8_t* sdS = sP + 2 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * TILE_BYTES);
+  uint8_t* sDQ = sdS + 2 * TILE_BYTES;  // 2 stages x 2 boxes of [128 rows x 32 f32], 128B-swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + 2 * BWD_DQ_STAGE);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;    // [2]
   uint64_t* q_empty = bars + 3;   // [2]
@@ -345,6 +369,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tmap_dq);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(sdp_full, 1);
@@ -403,6 +428,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           mbar_wait(pds_full, n & 1);
           tc_fence_after();
           const uint32_t aq = smem_u32(sQ + st * TILE_BYTES), ado = smem_u32(sdO + st * TILE_BYTES);
+          // dQ_i = dS K (contraction over the 128 keys) first: the compute warps turn it into the global
+          // reduce-add while dV / dK and the next S / dP are still on the tensor pipe
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            umma_bf16(tm_dq, make_sdesc(ads + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
+                      make_sdesc(ak + k * 2048, TILE_BYTES, 1024), id_q, k > 0);
+          }
+          umma_commit(dq_full);
           // contraction over the 128 query rows: 8 steps of 16 rows (2048 B per step in every tile)
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k) {
@@ -414,14 +447,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             umma_bf16(tm_dk, make_sdesc(ads + k * 2048, TILE_BYTES, 1024), make_sdesc(aq + k * 2048, TILE_BYTES, 1024),
                       id_kv, (n > 0 || k > 0) ? 1u : 0u);
           }
-          // dQ_i = dS K : contraction over the 128 keys
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            umma_bf16(tm_dq, make_sdesc(ads + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
-                      make_sdesc(ak + k * 2048, TILE_BYTES, 1024), id_q, k > 0);
-          }
           umma_commit(&q_empty[st]);
-          umma_commit(dq_full);
           if (n + 1 < n_iter) issue_sdp(n + 1);
         }
         umma_commit(fin_full);
@@ -436,16 +462,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint64_t groups_per_row = (p.T + 7) >> 3;
       const int n_iter = n_q - i_begin;
       const int kc0 = part * 32;
-      const uint32_t thr = p.drop.thresh << 16;
-      const float zs = p.drop.scale * p.scale;
+      const bool use_drop = p.drop.thresh != 0;
+      const DropState dst8(p.drop);
+      // keep-scale s = 1/(1-p) folded into the exponent: pr' = s * P.  With u = keep ? dP : 0:
+      //   P_drop = keep ? pr' : 0,   dS = P (s u - delta) c = pr' c (u - delta / s)
+      const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
+      const float inv_s = use_drop ? 1.f / p.drop.scale : 1.f;
+      const long long srow0 = (static_cast<long long>(b) * p.H + h) * p.T;
+      // per-row statistics of the next query block are fetched one iteration ahead
+      float lse_nx = INFINITY, dl_nx = 0.f;
+      if (n_iter > 0 && i_begin * BQ + r < p.T) {
+        lse_nx = __ldg(p.lse + srow0 + i_begin * BQ + r);
+        dl_nx = __ldg(p.delta + srow0 + i_begin * BQ + r);
+      }
       for (int n = 0; n < n_iter; ++n) {
         const int i = i_begin + n;
         const int q = i * BQ + r;
         const bool q_ok = q < p.T;
-        const long long sidx = (static_cast<long long>(b) * p.H + h) * p.T + q;
-        const float lse = q_ok ? p.lse[sidx] : INFINITY;  // +inf -> P = 0 for rows past the sequence end
-        const float dls = q_ok ? p.delta[sidx] * p.scale : 0.f;
-        const uint64_t row_id = static_cast<uint64_t>(sidx);
+        const float lse = lse_nx - lg_scale;  // +inf -> P = 0 for rows past the sequence end
+        const float dls = dl_nx * inv_s;
+        lse_nx = INFINITY; dl_nx = 0.f;
+        if (n + 1 < n_iter && q + BQ < p.T) {
+          lse_nx = __ldg(p.lse + srow0 + q + BQ);
+          dl_nx = __ldg(p.delta + srow0 + q + BQ);
+        }
+        const uint64_t row_id = static_cast<uint64_t>(srow0 + q);
         int lim = kv_len - k0;
         if (p.causal) lim = min(lim, q - k0 + 1);
         const bool full = __all_sync(0xffffffffu, lim >= BKV);
@@ -458,25 +499,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float pd[8], ds[8];
+          if (full) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            float pr = ex2_approx(fmaf(__uint_as_float(rs[g * 8 + t]), p.scale_log2, -lse));
-            if (!full) pr = (kc0 + g * 8 + t < lim) ? pr : 0.f;
-            pd[t] = pr;
+            for (int t = 0; t < 8; ++t) pd[t] = ex2_approx(fmaf(__uint_as_float(rs[g * 8 + t]), p.scale_log2, -lse));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              pd[t] = (kc0 + g * 8 + t < lim) ? ex2_approx(fmaf(__uint_as_float(rs[g * 8 + t]), p.scale_log2, -lse)) : 0.f;
           }
-          if (p.drop.thresh != 0) {
-            const uint4 bits = drop_bits8(p.drop, row_id * groups_per_row + ((k0 + kc0 + g * 8) >> 3));
-            const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+          if (use_drop) {
+            const uint4 bits = dst8.bits(row_id * groups_per_row + ((k0 + kc0 + g * 8) >> 3));
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              const bool keep = ((t & 1) ? w[t >> 1] : (w[t >> 1] << 16)) >= thr;
-              const float pr = pd[t];
-              ds[t] = pr * fmaf(__uint_as_float(rd[g * 8 + t]), keep ? zs : 0.f, -dls);
-              pd[t] = keep ? pr * p.drop.scale : 0.f;
+              const bool keep = dst8.keep(bits, t);
+              const float u = keep ? __uint_as_float(rd[g * 8 + t]) : 0.f;
+              ds[t] = (pd[t] * p.scale) * (u - dls);
+              pd[t] = keep ? pd[t] : 0.f;
             }
           } else {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) ds[t] = pd[t] * fmaf(__uint_as_float(rd[g * 8 + t]), p.scale, -dls);
+            for (int t = 0; t < 8; ++t) ds[t] = (pd[t] * p.scale) * (__uint_as_float(rd[g * 8 + t]) - dls);
           }
           const int kc = kc0 + g * 8;
           const uint32_t off = (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
@@ -486,25 +528,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(pds_full);
-        // dQ_i: this warp's 16 of the 64 head-dim columns
+        // dQ_i: this warp's 16 of the 64 head-dim columns -> fp32 staging tile -> one TMA reduce-add per
+        // 32-column box (full 128-byte lines into the fp32 dQ workspace instead of per-thread 16-byte REDs)
         mbar_wait(dq_full, n & 1);
         tc_fence_after();
         {
           uint32_t rq[16];
           tmem_ld16(tm_dq + lane_off + part * 16, rq);
           tmem_ld_wait();
-          if (q_ok) {
-            float* dst = p.dq_acc + (static_cast<long long>(b) * p.T + q) * p.E + h * HD + part * 16;
+          uint8_t* box = sDQ + (n & 1) * BWD_DQ_STAGE + (part >> 1) * (128 * 128);
 #pragma unroll
-            for (int t = 0; t < 16; t += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + t), "f"(__uint_as_float(rq[t])),
-                           "f"(__uint_as_float(rq[t + 1])), "f"(__uint_as_float(rq[t + 2])),
-                           "f"(__uint_as_float(rq[t + 3]))
-                           : "memory");
-          }
+          for (int t = 0; t < 4; ++t)
+            *reinterpret_cast<uint4*>(box + r * 128 + ((((part & 1) * 4 + t) ^ (r & 7)) << 4)) =
+                make_uint4(rq[4 * t], rq[4 * t + 1], rq[4 * t + 2], rq[4 * t + 3]);
         }
         tc_fence_before();
+        fence_proxy_async_smem();
+        // the group issued one iteration ago has long finished reading the other stage: waiting for it here,
+        // before the barrier, tells every thread that the stage written next iteration is free
+        if (threadIdx.x == 0) bulk_wait_read0();
+        bar_sync(1, 512);
+        if (threadIdx.x == 0) {
+          const uint8_t* src = sDQ + (n & 1) * BWD_DQ_STAGE;
+          tma_reduce_add_3d(&tmap_dq, src, h * HD, i * BQ, b);
+          tma_reduce_add_3d(&tmap_dq, src + 128 * 128, h * HD + 32, i * BQ, b);
+          bulk_commit();
+        }
       }
+      if (threadIdx.x == 0) bulk_wait0();
       // final dK / dV: row r = key k0 + r, this warp's 16 head-dim columns
       mbar_wait(fin_full, 0);
       tc_fence_after();
@@ -600,13 +651,18 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   if (rc) return rc;
   rc = make_tmap_3d(&tdo, dout, E, T, B, E, static_cast<long long>(T) * E, HD, BQ);
   if (rc) return rc;
+  CUtensorMap tdq;
+  rc = make_tmap_3d(&tdq, dq_acc, E, T, B, E, static_cast<long long>(T) * E, 32, BQ, 4);
+  if (rc) return rc;
   static bool configured = false;
   if (!configured) {
     MH_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     configured = true;
   }
   const long long pairs = rows * heads;
-  attn_delta_kernel<<<static_cast<int>((pairs + 7) / 8), 256, 0, st>>>(
+  long long dgrid = (pairs * 8 + 255) / 256;
+  if (dgrid > static_cast<long long>(sm_count()) * 16) dgrid = static_cast<long long>(sm_count()) * 16;
+  attn_delta_kernel<<<static_cast<int>(dgrid), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T, heads);
   MH_LAUNCH_CHECK();
   ++g_launches;
@@ -617,7 +673,7 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
   p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop(p_drop, seed, site);
-  attn_bwd_kernel<<<dim3((T + BKV - 1) / BKV, heads, B), BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, p);
+  attn_bwd_kernel<<<dim3((T + BKV - 1) / BKV, heads, B), BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, tdq, p);
   MH_LAUNCH_CHECK();
   ++g_launches;
   long long g = (rows * (E / 8) + 255) / 256;

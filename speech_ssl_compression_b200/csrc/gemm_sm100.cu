@@ -375,16 +375,17 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
 
 // 3-D variant used by attention: [d2][d1][d0] with strides in elements.
 int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
-                 long long stride2, int box0, int box1) {
+                 long long stride2, int box0, int box1, int elem_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
-  MH_CHECK(stride1 % 8 == 0 && stride2 % 8 == 0, "TMA strides must be multiples of 8 elements");
+  MH_CHECK((stride1 * elem_bytes) % 16 == 0 && (stride2 * elem_bytes) % 16 == 0, "TMA strides must be multiples of 16 bytes");
   cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
-  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1) * 2, static_cast<cuuint64_t>(stride2) * 2};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1) * elem_bytes, static_cast<cuuint64_t>(stride2) * elem_bytes};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with %d", static_cast<int>(r));

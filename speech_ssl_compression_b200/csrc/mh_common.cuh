@@ -105,6 +105,39 @@ __device__ __forceinline__ void drop_apply8(const DropCfg& d, uint64_t group, fl
   }
 }
 
+// Per-thread dropout state for instruction-bound inner loops: the 7 Philox round keys live in registers
+// (seed + device counter folded in once), so a call is 14 IMAD.WIDE + 14 LOP3 for 8 decisions.
+struct DropState {
+  uint32_t ka[7], kb[7];
+  uint32_t site, thr;  // thr = thresh << 16 (0 => disabled)
+  __device__ __forceinline__ explicit DropState(const DropCfg& d) {
+    const uint64_t seed = d.seed + (d.offset != nullptr ? 0x9E3779B97F4A7C15ull * __ldg(d.offset) : 0ull);
+    uint32_t a = static_cast<uint32_t>(seed), b = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 7; ++r) { ka[r] = a; kb[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    site = d.site;
+    thr = d.thresh << 16;
+  }
+  // same stream as drop_bits8(cfg, group)
+  __device__ __forceinline__ uint4 bits(uint64_t group) const {
+    uint32_t c0 = static_cast<uint32_t>(group), c1 = static_cast<uint32_t>(group >> 32), c2 = site, c3 = 0x9E3779B9u;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+      const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+      const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ ka[r], n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ kb[r];
+      c1 = static_cast<uint32_t>(p1); c3 = static_cast<uint32_t>(p0);
+      c0 = n0; c2 = n2;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  // keep decision of element j (0..7) of the group whose bits are `r`
+  __device__ __forceinline__ bool keep(const uint4& r, int j) const {
+    const uint32_t w = j < 2 ? r.x : (j < 4 ? r.y : (j < 6 ? r.z : r.w));
+    return ((j & 1) ? w : (w << 16)) >= thr;
+  }
+};
+
 // ---- math ----
 // erf-GELU in fp32 (fairseq_code/gelu.py:34-35) without erff():
 //   erfc(a / sqrt 2) = 2^-g(a),  g(a) ~= a (c0 + c1 a + c2 a^2 + c3 a^3 + c4 a^4)  (least-squares fit on

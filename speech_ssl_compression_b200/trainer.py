@@ -161,8 +161,10 @@ class TrainStep:
         ops.bump_weight_epoch()
         self.graph = torch.cuda.CUDAGraph()
         n0 = K.L.launch_count()
-        with torch.cuda.graph(self.graph):
+        rng_state = np.random.get_state()  # the per-layer layer-drop draws of the captured forward are replayed
+        with torch.cuda.graph(self.graph):  # by run(); capturing must not advance the host stream
             self._body()
+        np.random.set_state(rng_state)
         self.launches_per_step = K.L.launch_count() - n0
         return self
 

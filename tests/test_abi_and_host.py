@@ -1,0 +1,219 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/mh_b200.h declares (no
+compute calls without a GPU), and the host-side mirror of the reference (config defaults, parameter
+names + random init, span masks, prune selections, checkpoint surgery) matches the reference goldens."""
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+import tempfile
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import melhubert_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "speech_ssl_compression_b200")
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ---------------------------------------------------------------------------------------------- ABI
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mh_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mh_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    so = os.path.join(PKG, "libmh_b200.so")
+    if not os.path.isfile(so):
+        subprocess.run(["make", "-C", os.path.join(PKG, "csrc"), "-j", str(os.cpu_count() or 4)], check=True)
+    lib = ctypes.CDLL(so)
+    names = _declared_symbols()
+    assert len(names) >= 40, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.mh_version() >= 100
+    lib.mh_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.mh_last_error(), bytes)
+
+
+def test_header_cites_the_reference_for_every_kernel_family():
+    text = open(os.path.join(ROOT, "include", "mh_b200.h")).read()
+    for cite in ("forward_multihead_attention.py", "module.py", "model.py", "pretrain_expert.py", "prune.py", "runner.py"):
+        assert cite in text, cite
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import it."""
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_model_refuses_cpu_tensors():
+    from speech_ssl_compression_b200.model import MelHuBERTConfig, MelHuBERTModel
+
+    m = MelHuBERTModel(MelHuBERTConfig(dict(feat_emb_dim=80, encoder_layers=1)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 16, 80), torch.ones(1, 16))
+
+
+# ------------------------------------------------------------------------------- config / init parity
+def test_config_defaults_match_reference():
+    from speech_ssl_compression_b200.model_config import MelHuBERTConfig
+
+    c = MelHuBERTConfig({})
+    assert (c.feat_emb_dim, c.encoder_layers, c.encoder_embed_dim, c.encoder_ffn_embed_dim, c.encoder_attention_heads) == (40, 1, 768, 3072, 12)
+    assert (c.mask_prob, c.mask_length, c.num_cluster, c.skip_nomask, c.skip_masked) == (0.8, 10, 512, True, False)
+    assert (c.dropout, c.attention_dropout, c.activation_dropout, c.encoder_layerdrop) == (0.1, 0.1, 0.1, 0.0)
+    assert (c.conv_pos, c.conv_pos_groups, c.layer_norm_first, c.mask_before_proj) == (128, 16, False, True)
+
+
+def test_random_init_is_bit_identical_to_the_reference(golden):
+    """Same construction order + init_bert_params on the CPU generator -> the seed-1337 weights of the
+    reference model (fixture init_1337.npz: parameter names and sha256 of the raw fp32 bytes)."""
+    import random
+
+    from speech_ssl_compression_b200.model import MelHuBERTConfig, MelHuBERTModel
+
+    g = golden("init_1337")
+    random.seed(1337); np.random.seed(1337); torch.manual_seed(1337)
+    m = MelHuBERTModel(MelHuBERTConfig(dict(feat_emb_dim=80, encoder_layers=12, mask_prob=0.7, mask_length=5)))
+    sd = m.state_dict()
+    names = [str(n) for n in g["names"]]
+    assert sorted(sd.keys()) == sorted(names)                                # state_dict key set
+    assert sum(p.numel() for p in m.parameters()) == int(g["nparams"][0])
+    got = [sha16(sd[n].numpy()) for n in names]
+    want = [str(h) for h in g["hashes"]]
+    bad = [n for n, a, b in zip(names, got, want) if a != b]
+    assert not bad, bad[:5]
+
+
+# ------------------------------------------------------------------------------------- span masks
+@pytest.mark.parametrize("case", ["c20", "c10", "short", "e1"])
+def test_span_mask_host_generator_bit_exact(golden, case):
+    from speech_ssl_compression_b200.fairseq_code import compute_mask_indices
+
+    g = golden("span_mask")
+    shp = g[case + "_shape"]
+    b, t, p, ml = int(shp[0]), int(shp[1]), shp[2] / 1000.0, int(shp[3])
+    lens = [int(x) for x in shp[4:]]
+    np.random.seed(1337)
+    m = compute_mask_indices((b, t), None, p, ml, "static", 0.0, min_masks=2, no_overlap=False, min_space=1,
+                             require_same_masks=False, valid_lens=lens)
+    nxt = np.random.rand()
+    assert np.array_equal(np.packbits(m), g[case + "_mask"])
+    assert nxt == g[case + "_next"][0]                                      # same RNG consumption
+    # the padding-mask door (what the reference call site passes) gives the same mask
+    pm = torch.zeros(b, t, dtype=torch.bool)
+    for i, l in enumerate(lens):
+        pm[i, l:] = True
+    np.random.seed(1337)
+    m2 = compute_mask_indices((b, t), pm, p, ml, "static", 0.0, min_masks=2, require_same_masks=False)
+    assert np.array_equal(m, m2)
+
+
+# ------------------------------------------------------------------ pruning objects on CPU tensors
+class _Holder:
+    def __init__(self, model, cfg):
+        self.model, self.upstream_config, self.pruned_heads = model, {"melhubert": cfg}, None
+
+
+def _cfg(frame, layers):
+    return dict(feat_emb_dim=80 if frame == 20 else 40, encoder_layers=layers, mask_prob=0.7,
+                mask_length=5 if frame == 20 else 10)
+
+
+@pytest.mark.parametrize("target", ["by_layer", "by_whole"])
+def test_head_pruning_tools_selection_bit_exact_on_cpu(golden, target):
+    from speech_ssl_compression_b200.head_pruning.hp_utils import HeadPruningTools
+    from speech_ssl_compression_b200.model import MelHuBERTConfig, MelHuBERTModel
+
+    g = golden("head_prune")
+    cfg = _cfg(10, 12)
+    m = MelHuBERTModel(MelHuBERTConfig(cfg))
+    m.load_state_dict(O.synth_state_dict(cfg, seed=11))
+    rc = {"prune": {"metric": "l1", "target": target, "total_steps": 11, "num_heads_each_step": 12}}
+    tools = HeadPruningTools(Namespace(expdir=tempfile.mkdtemp(), device="cpu"), rc, {"melhubert": cfg}, _Holder(m, cfg))
+    s0 = np.array([s for _, s in tools.get_heads_norm(m.encoder)])
+    np.testing.assert_allclose(s0, g[f"{target}_scores0"], rtol=1e-6)
+    for _ in range(3):
+        tools.prune_api()
+    rec = [(s, l, h) for s, grp in enumerate(tools.pruned_heads) for l, hs in grp.items() for h in hs]
+    assert np.array_equal(np.array(rec), g[f"{target}_record"])
+    assert [l.self_attn.num_heads for l in m.encoder.layers] == g[f"{target}_heads"].tolist()
+    # sliced tensors equal the oracle's slicing of the same state dict
+    sd = O.synth_state_dict(cfg, seed=11)
+    for step_grp in tools.pruned_heads:
+        for l, hs in step_grp.items():
+            O.slice_heads(sd, l, hs)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_row_pruning_tools_selection_bit_exact_on_cpu(golden):
+    from speech_ssl_compression_b200.model import MelHuBERTConfig, MelHuBERTModel
+    from speech_ssl_compression_b200.row_pruning.rp_utils import RowPruningTools
+
+    g = golden("row_prune")
+    cfg = _cfg(20, 4)
+    m = MelHuBERTModel(MelHuBERTConfig(cfg))
+    m.load_state_dict(O.synth_state_dict(cfg, seed=13))
+    holder = _Holder(m, cfg)
+    rc = {"prune": {"num_rows_each_step": 128, "total_steps": 20}}
+    tools = RowPruningTools(Namespace(expdir=tempfile.mkdtemp(), device="cpu"), rc, {"melhubert": cfg}, holder)
+    for step in range(2):
+        tools.prune_api()
+        assert [sha16(l.fc1.bias.detach().numpy()) for l in m.encoder.layers] == [str(x) for x in g["bias_hash"][step]]
+    assert holder.upstream_config["melhubert"]["encoder_ffn_embed_dim"] == 3072 - 256 == m.encoder.ffn_embedding_dim
+
+
+def test_weight_pruning_reparam_contract_on_cpu(golden):
+    """*_orig / *_mask key set, bool masks, Identity -> L1 -> remove life cycle (prune.py:190-296)."""
+    from speech_ssl_compression_b200.model import MelHuBERTConfig, MelHuBERTModel
+    from speech_ssl_compression_b200.pytorch_code import prune
+    from speech_ssl_compression_b200.weight_pruning.wp_utils import get_params_to_prune
+
+    g = golden("weight_prune")
+    cfg = _cfg(20, 12)
+    m = MelHuBERTModel(MelHuBERTConfig(cfg))
+    params, is_prunable = get_params_to_prune(m)
+    assert len(params) == 144 and is_prunable("encoder.layers.3.fc1.weight") and not is_prunable("final_proj.weight")
+    prune.global_unstructured(params, pruning_method=prune.Identity)
+    assert sorted(m.state_dict().keys()) == [str(x) for x in g["keys_identity"]]
+    assert prune.is_pruned(m)
+    fc1 = m.encoder.layers[0].fc1
+    w_param = fc1.weight_orig
+    assert fc1.weight_mask.dtype == torch.bool and bool(fc1.weight_mask.all())
+    small = [(fc1, "weight"), (fc1, "bias")]
+    for mod, name in small:
+        prune.remove(mod, name)
+    assert fc1.weight is w_param                                             # same Parameter object survives remove()
+    prune.global_unstructured(small, pruning_method=prune.L1Unstructured, amount=0.5)
+    total = fc1.weight_orig.numel() + fc1.bias_orig.numel()
+    pruned = int((~fc1.weight_mask).sum()) + int((~fc1.bias_mask).sum())
+    assert pruned == int(round(0.5 * total))
+    ref_masks, k, thr, ties = O.global_l1_masks([fc1.weight_orig.detach(), fc1.bias_orig.detach()], 0.5)
+    if ties <= 1:
+        assert torch.equal(fc1.weight_mask, ref_masks[0]) and torch.equal(fc1.bias_mask, ref_masks[1])
+    assert torch.equal(fc1.weight, fc1.weight_orig.masked_fill(~fc1.weight_mask, 0))
+
+
+def test_flac_decoder_known_answer():
+    """STREAMINFO MD5 of the two example files == MD5 of the decoded PCM."""
+    from speech_ssl_compression_b200.frontend.flac import decode_flac
+
+    want = {"100-121669-0000.flac": ("1f9b4b53e3c194f950f62649f7147a05", 32640),
+            "1001-134707-0000.flac": ("903a2666cf9765de9bb270fdd3fe1f08", 253280)}
+    for fn, (md5, n) in want.items():
+        pcm, sr, ok, hexd = decode_flac(os.path.join(ROOT, "tests", "golden", "example", fn))
+        assert ok and hexd == md5 and sr == 16000 and len(pcm) == n

@@ -180,7 +180,7 @@ def workload_config(args, per_gpu_batch=None):
                         f"(reference: 4 utterances x 8 accumulation micro-batches per optimizer step), dropout 0.1",
             "per_gpu_batch": B, "frames": args.frames, "global_batch": B * args.gpus, "parallelism": f"dp{args.gpus}",
             "l2": "per-step working set (several GB of activations) >> 126 MB L2, no flush needed",
-            "cuda_graph": not args.no_graph}
+            "cuda_graph": (not args.no_graph) and args.gpus == 1}
 
 
 def live_gemm_roofline(ts, batch, peaks):
@@ -328,14 +328,12 @@ def main():
 
     # ---- roofline of the dominant kernel family (the tcgen05 GEMM: ~45 % of the step), measured LIVE inside
     #      one extra eager optimizer step: a CUDA-event pair around every mh_gemm launch on the launching stream
-    roof = None
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        roof = live_gemm_roofline(ts, batches[0], peaks)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = live_gemm_roofline(ts, batches[0], peaks)  # every rank runs it: the step contains collectives
     if rank != 0:
         dist.barrier()
         return
@@ -349,7 +347,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": ts.h2d_bytes, "d2h_bytes_per_step": ts.d2h_bytes},
-        "gpu_launches": int(ts.launches_per_step * args.steps if not args.no_graph else eager_launches),
+        "gpu_launches": int(ts.launches_per_step * args.steps if ts.use_graph else eager_launches),
         "launches_per_step": int(ts.launches_per_step),
         "clocks": clocks,
         "roofline": roof,

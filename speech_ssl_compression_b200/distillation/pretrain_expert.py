@@ -109,7 +109,7 @@ class MelHuBERTDistiller(nn.Module):
             total, h, s, t = self.loss_fn_kd(s_out[1], s_out[3], t_out[1], T=self.loss_temp, alpha=self.loss_alpha)
         else:
             total, h, s, t = self.loss_fn_kd(s_out[2], s_out[4], t_out[2], T=self.loss_temp, alpha=self.loss_alpha)
-        self.last_terms = (h, s, t)
+        self.last_terms = (h.detach(), s.detach(), t.detach())
         return total, 1
 
 

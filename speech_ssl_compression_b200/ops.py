@@ -450,8 +450,9 @@ class KDLossFn(torch.autograd.Function):
         K.kd_finalize(acc, alpha, out[0:4], out[4:5], out[5:6])
         ctx.save_for_backward(s_logits, t_logits, labels, n_valid, out)
         ctx.T = T
-        ctx.mark_non_differentiable(out)
-        return out[0].clone(), out[0:4]
+        terms = out[0:4].clone()  # detached diagnostics: must not keep the autograd graph (and its
+        ctx.mark_non_differentiable(terms)  # stream-bound grad accumulators) alive across steps
+        return out[0].clone(), terms
 
     @staticmethod
     def backward(ctx, dloss, _):

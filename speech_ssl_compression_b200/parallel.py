@@ -71,9 +71,6 @@ class DataParallelB200:
         self.flat = None
         self._pending = []
         self._comm_stream = None
-        if self.enabled:
-            for p in model.parameters():  # identical start on every rank
-                dist.broadcast(p.data, src=0)
 
     # -- loss normaliser ---------------------------------------------------------------------
     def all_reduce_sum(self, t):
@@ -85,6 +82,8 @@ class DataParallelB200:
     def attach(self, flat: FlatBuffers):
         """Register the flat gradient buffer and hook every encoder layer's backward."""
         self.flat = flat
+        if self.enabled:  # identical start on every rank: one broadcast of the whole flat parameter buffer
+            dist.broadcast(flat.flat_param, src=0)
         self._layer_spans = []
         covered = []
         for layer in self.model.encoder.layers:

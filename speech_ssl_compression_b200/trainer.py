@@ -5,6 +5,8 @@ clip + Adam), which removes Python / launch overhead from the hot loop.
 Mirrors what reference ``runner.py:357-427`` does per optimizer step: forward -> loss / accum
 -> backward -> grads /= n -> clip_grad_norm_ -> Adam.step -> zero_grad.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -85,6 +87,10 @@ class TrainStep:
         self.dp = getattr(expert, "dp", None)
         if self.dp is not None:
             self.dp.attach(self.flat)
+            if self.dp.enabled and use_graph and os.environ.get("MH_DP_GRAPH", "0") != "1":
+                # NCCL collectives on a side stream inside a captured autograd backward trip stream-capture
+                # isolation in torch 2.11; data-parallel steps run eagerly (the step is GPU-bound either way)
+                use_graph = False
         dev = self.device
         self.feat = torch.zeros(B, T, D, device=dev)
         self.label = torch.zeros(B, T, device=dev, dtype=torch.int64)

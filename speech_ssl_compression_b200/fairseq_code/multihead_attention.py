@@ -34,7 +34,7 @@ class FairseqDropout(nn.Module):
 
 class _SelfAttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, kv_len, mha, B, T, seed, site, causal, *params):
+    def forward(ctx, x, kv_len, mha, B, T, seed, site, causal, hook):
         heads = mha.num_heads
         p_att = mha.dropout_module.p if (mha.training or mha.dropout_module.apply_during_inference) else 0.0
         wqkv, bqkv = ops.packed_operands(mha, "qkv", [mha.q_proj, mha.k_proj, mha.v_proj])
@@ -130,5 +130,5 @@ class MultiheadAttention(nn.Module):
         x = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
         self._rng_calls += 1
         out = _SelfAttentionFn.apply(x.contiguous(), valid_lens, self, B, T, self._rng_calls, 0, attn_mask is not None,
-                                     *list(self.parameters()))
+                                     ops.grad_hook(self, x.device))
         return out.view(B, T, -1).transpose(0, 1).to(query.dtype), None

@@ -72,6 +72,20 @@ def packed_operands(owner, key, linears):
     return wbuf, bbuf
 
 
+def grad_hook(module_or_params, device):
+    """A fresh zero-size leaf that stands in for a module's parameters in the autograd graph.
+
+    The fused functions write parameter gradients in place (wgrad epilogues reduce-add into ``param.grad``), so
+    the parameters themselves never need to be autograd inputs; passing them would also tie the graph to their
+    long-lived AccumulateGrad nodes, whose creation stream breaks CUDA-graph capture once any other tensor
+    (e.g. the ``weight = weight_orig * mask`` buffer of pytorch_code.prune) has kept them alive.  The hook is
+    only created when some parameter is trainable, so frozen models (the distillation teacher) build no graph."""
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return torch.empty(0, device=device, requires_grad=True)
+    return None
+
+
 def _grad_of(p):
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
@@ -101,7 +115,7 @@ def _wgrad(dy, x, lin, col0=0, ncols=None):
 # ---------------------------------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, lin, *params):
+    def forward(ctx, x, lin, hook):
         w, bias = packed_operands(lin, "self", [lin])
         out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=bf16)
         K.gemm(x, w, out, bias=bias)
@@ -118,12 +132,12 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             K.gemm(dy, w, dx, b_mn=True)
-        return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+        return dx, None, None
 
 
 def linear(x, lin):
     """y = x @ W^T + b on the tcgen05 GEMM.  x: bf16 [rows, in_features]."""
-    return LinearFn.apply(x, lin, *[p for p in lin.parameters()])
+    return LinearFn.apply(x, lin, grad_hook(lin, x.device))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -131,8 +145,8 @@ def linear(x, lin):
 # ---------------------------------------------------------------------------------------------
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ln, p_drop, seed, site, gamma, beta):
-        y, mean, rstd = K.layernorm_fwd(x, gamma.detach(), beta.detach(), ln.eps, p_drop=p_drop, seed=seed, site=site)
+    def forward(ctx, x, ln, p_drop, seed, site, hook):
+        y, mean, rstd = K.layernorm_fwd(x, ln.weight.detach(), ln.bias.detach(), ln.eps, p_drop=p_drop, seed=seed, site=site)
         ctx.ln, ctx.drop = ln, (p_drop, seed, site)
         ctx.save_for_backward(x, mean, rstd)
         return y
@@ -144,11 +158,11 @@ class LayerNormFn(torch.autograd.Function):
         p, seed, site = ctx.drop
         dx, _ = K.layernorm_bwd(dy.contiguous(), x, ln.weight.detach(), mean, rstd, _grad_of(ln.weight), _grad_of(ln.bias),
                                 p_in=p, seed_in=seed, site_in=site)
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 def layer_norm(x, ln, p_drop=0.0, seed=0, site=0):
-    return LayerNormFn.apply(x, ln, p_drop, seed, site, ln.weight, ln.bias)
+    return LayerNormFn.apply(x, ln, p_drop, seed, site, grad_hook(ln, x.device))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -177,7 +191,7 @@ class PosConvFn(torch.autograd.Function):
     """rows [B*T, C] bf16 -> rows + gelu(conv(rows) + bias); implicit-GEMM tcgen05 kernels fwd / dgrad / wgrad."""
 
     @staticmethod
-    def forward(ctx, x, conv, B, T, *params):
+    def forward(ctx, x, conv, B, T, hook):
         w_fwd, w_bwd, norm = _posconv_operands(conv)
         need = any(ctx.needs_input_grad)
         y, z = K.posconv_fwd(x, w_fwd, conv.bias.detach(), B, T, conv.groups, 128, want_z=need)
@@ -205,7 +219,7 @@ class PosConvFn(torch.autograd.Function):
 
 
 def pos_conv(x, conv, B, T):
-    return PosConvFn.apply(x, conv, B, T, *[p for p in conv.parameters()])
+    return PosConvFn.apply(x, conv, B, T, grad_hook(conv, x.device))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -219,7 +233,7 @@ class EncoderLayerFn(torch.autograd.Function):
     """x [B*T, C] bf16 -> layer output [B*T, C] bf16 (post-LN or pre-LN block)."""
 
     @staticmethod
-    def forward(ctx, x, kv_len, layer, B, T, seed, site_base, causal, *params):
+    def forward(ctx, x, kv_len, layer, B, T, seed, site_base, causal, hook):
         mha = layer.self_attn
         heads = mha.num_heads
         training = layer.training
@@ -333,8 +347,7 @@ class EncoderLayerFn(torch.autograd.Function):
 
 
 def encoder_layer(x, kv_len, layer, B, T, seed, site_base, causal=False):
-    params = [p for p in layer.parameters()]
-    return EncoderLayerFn.apply(x, kv_len, layer, B, T, seed, site_base, causal, *params)
+    return EncoderLayerFn.apply(x, kv_len, layer, B, T, seed, site_base, causal, grad_hook(layer, x.device))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ typedef struct {
   long long ld_aux;
   const uint8_t* mask;       /* MH_EPI_F32: 0/1 bytes [M, ldd] or NULL */
   float p_drop; uint64_t seed; uint32_t site;   /* dropout stream (see mh_common.cuh) */
-  int block_n;               /* 0 = auto, else 128 or 256 */
+  int block_n;               /* 0 = auto; 128 / 256 = single-CTA 128 x block_n tiles; -256 = CTA-pair (cta_group::2) 256 x 256 tiles */
   int split_k;               /* 0 = auto (MH_EPI_F32 only), else number of K splits */
 } mh_gemm_args;
 

@@ -19,6 +19,8 @@
 // Operands may be K-major (row = m or n, 64 contiguous k) or MN-major (row = k, 64 contiguous m or n); the
 // latter is what wgrad (dW = dY^T X) needs and avoids any transpose kernel.  MH_EPI_F32 accumulates with
 // cp.reduce.async.bulk (.add.f32), which makes split-K and gradient accumulation the same code path.
+#include <stdlib.h>
+
 #include "mh_b200.h"
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
@@ -62,17 +64,210 @@ __device__ __forceinline__ uint32_t stg_off(int r, int ch) {
   return r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one output tile (128 accumulator rows of this CTA x BN columns), shared by the 1-CTA and the
+// CTA-pair kernels.  Executed by the 16 epilogue warps; see the header comment for the data flow.
+// ---------------------------------------------------------------------------------------------
+struct EpiThread {
+  int quad, grp, lane, r_tile, bar_id;
+  bool leader;
+  uint8_t* stg;
+  uint32_t lane_off;
+};
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmD, const CUtensorMap* tmAuxIn,
+                                              const CUtensorMap* tmAuxOut, const EpiThread& e, uint32_t tmem_acc, int m0,
+                                              int n0, bool has_k, uint64_t* tfull_bar, uint32_t acc_phase, uint64_t* aux_bar,
+                                              uint32_t& aux_phase, uint32_t tempty_cluster_addr) {
+  constexpr bool OUT_F32 = EPI == MH_EPI_F32;
+  constexpr bool HAS_AUX_IN = EPI == MH_EPI_RES || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD;
+  constexpr int CG = BN / EPI_GROUPS;                    // columns per epilogue group
+  constexpr int SUBC = OUT_F32 ? 32 : CG;                // columns staged per pass (a staging row is <= 128 bytes)
+  constexpr int ROWB = SUBC * (OUT_F32 ? 4 : 2);         // staging row bytes
+  static_assert(ROWB == 64 || ROWB == 128, "staging rows are 64 or 128 bytes");
+  const int gcol0 = n0 + e.grp * CG;
+  const bool active = gcol0 < p.N && has_k;  // uniform over the group
+  const long long row = m0 + e.r_tile;
+  uint8_t* stg = e.stg;
+
+  // (1) the staging tile is free once the previous TMA store has read it; residual / pre-activation
+  //     tiles are fetched into it right away so the load overlaps the wait for the accumulator
+  if (e.leader) {
+    bulk_wait_read0();
+    if (HAS_AUX_IN && active) {
+      mbar_expect_tx(aux_bar, 128 * ROWB);
+      tma_load_2d(stg, tmAuxIn, aux_bar, gcol0, m0);
+    }
+  }
+  if (HAS_AUX_IN) {
+    if (active) {
+      mbar_wait(aux_bar, aux_phase);
+      aux_phase ^= 1;
+    }
+  } else {
+    bar_sync(e.bar_id, 128);
+  }
+
+  // (2) accumulator -> registers -> staging
+  mbar_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+  if (OUT_F32) {
+    // fp32 reduce-add (weight gradients): 32 columns per pass through the 16 KB staging tile
+#pragma unroll 1
+    for (int s = 0; s < CG / 32; ++s) {
+      const int col_in_tile = e.grp * CG + s * 32;
+      const bool sub_active = active && (n0 + col_in_tile) < p.N;
+      if (s > 0) {
+        if (e.leader) bulk_wait_read0();
+        bar_sync(e.bar_id, 128);
+      }
+      if (sub_active) {
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + e.lane_off + col_in_tile, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = n0 + col_in_tile + q * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+          if (p.mask != nullptr && col < p.N && row < p.M) {
+            const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + row * p.ldd + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (((mk.x >> (8 * j)) & 0xFF) == 0) v[j] = 0.f;
+              if (((mk.y >> (8 * j)) & 0xFF) == 0) v[4 + j] = 0.f;
+            }
+          }
+          *reinterpret_cast<float4*>(stg + stg_off<ROWB>(e.r_tile, 2 * q)) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(stg + stg_off<ROWB>(e.r_tile, 2 * q + 1)) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      if (s == CG / 32 - 1) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (e.lane == 0) mbar_arrive_cluster(tempty_cluster_addr);
+      }
+      if (sub_active) {
+        fence_proxy_async_smem();
+        bar_sync(e.bar_id, 128);
+        if (e.leader) {
+          tma_reduce_add_2d(tmD, stg, n0 + col_in_tile, m0);
+          bulk_commit();
+        }
+      }
+    }
+    return;
+  }
+
+  uint4 held[CG / 8];  // GELU with two outputs: activated values wait here while `pre` is stored
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < CG / 32; ++s) {
+      const int col_in_tile = e.grp * CG + s * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + e.lane_off + col_in_tile, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = n0 + col_in_tile + q * 8;
+        const bool col_ok = col < p.N;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+        const int ch = s * 4 + q;  // 16-byte chunk of the staging row
+        uint8_t* slot = stg + stg_off<ROWB>(e.r_tile, ch);
+        if (EPI == MH_EPI_BF16 || EPI == MH_EPI_GELU || EPI == MH_EPI_RES) {
+          if (p.bias != nullptr && col_ok) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+        }
+        if (EPI == MH_EPI_GELU) {
+          // the reference evaluates GELU in fp32 on the half-precision fc1 output
+          // (fairseq_code/gelu.py:35 under autocast): round first, then activate.
+          const uint4 pre = f32_to_bf16x8(v);
+          if (p.has_aux_out) *reinterpret_cast<uint4*>(slot) = pre;
+          bf16x8_to_f32(pre, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (EPI == MH_EPI_DGELU) {
+          float pre[8];
+          bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), pre);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
+        }
+        if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
+          if (p.drop.thresh != 0)
+            drop_apply8(p.drop, static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + (col >> 3), v);
+        }
+        if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
+          float a[8];
+          bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += a[j];
+        }
+        const uint4 o = f32_to_bf16x8(v);
+        if (EPI == MH_EPI_GELU && p.has_aux_out) held[ch] = o;
+        else *reinterpret_cast<uint4*>(slot) = o;
+      }
+    }
+  }
+  // (3) TMEM buffer back to the MMA warp
+  tc_fence_before();
+  __syncwarp();
+  if (e.lane == 0) mbar_arrive_cluster(tempty_cluster_addr);
+
+  // (4) staging -> global
+  if (active) {
+    fence_proxy_async_smem();
+    bar_sync(e.bar_id, 128);
+    if (EPI == MH_EPI_GELU && p.has_aux_out) {
+      if (e.leader) {
+        tma_store_2d(tmAuxOut, stg, gcol0, m0);
+        bulk_commit();
+        bulk_wait_read0();
+      }
+      bar_sync(e.bar_id, 128);
+#pragma unroll
+      for (int ch = 0; ch < CG / 8; ++ch) *reinterpret_cast<uint4*>(stg + stg_off<ROWB>(e.r_tile, ch)) = held[ch];
+      fence_proxy_async_smem();
+      bar_sync(e.bar_id, 128);
+    }
+    if (e.leader) {
+      tma_store_2d(tmD, stg, gcol0, m0);
+      bulk_commit();
+    }
+  }
+}
+
+__device__ __forceinline__ EpiThread make_epi_thread(int warp, int lane, uint8_t* staging) {
+  EpiThread e;
+  e.quad = warp & 3;   // TMEM lane quadrant
+  e.grp = warp >> 2;   // column group
+  e.lane = lane;
+  e.r_tile = e.quad * 32 + lane;
+  e.bar_id = 1 + e.grp;
+  e.leader = e.quad == 0 && lane == 0;
+  e.stg = staging + e.grp * STG_CHUNK;
+  e.lane_off = static_cast<uint32_t>(e.quad * 32) << 16;
+  return e;
+}
+
 template <int BN, int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
             const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
   using Cfg = TileCfg<BN>;
-  constexpr bool OUT_F32 = EPI == MH_EPI_F32;
-  constexpr bool HAS_AUX_IN = EPI == MH_EPI_RES || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD;
-  constexpr int CG = BN / EPI_GROUPS;              // columns per epilogue group
-  constexpr int ROWB = CG * (OUT_F32 ? 4 : 2);     // staging row bytes
-  static_assert(ROWB == 64 || ROWB == 128, "fp32 output needs BN = 128");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -189,14 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------- epilogue warps
-    const int quad = warp & 3;         // TMEM lane quadrant
-    const int grp = warp >> 2;         // column group
-    const int r_tile = quad * 32 + lane;
-    const bool leader = quad == 0 && lane == 0;
-    uint8_t* stg = staging + grp * STG_CHUNK;
-    const int bar_id = 1 + grp;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const EpiThread e = make_epi_thread(warp, lane, staging);
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -204,135 +392,212 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
       const int kb0 = (tile % splits) * kb_per_split;
       const bool has_k = kb0 < kblocks_total;  // empty split (possible when splits does not divide)
-      const int gcol0 = n0 + grp * CG;
-      const bool active = gcol0 < p.N && has_k;  // uniform over the group
-      const long long row = m0 + r_tile;
-
-      // (1) the staging tile is free once the previous TMA store has read it; residual / pre-activation
-      //     tiles are fetched into it right away so the load overlaps the wait for the accumulator
-      if (leader) {
-        bulk_wait_read0();
-        if (HAS_AUX_IN && active) {
-          mbar_expect_tx(&aux_full[grp], 128 * ROWB);
-          tma_load_2d(stg, &tmAuxIn, &aux_full[grp], gcol0, m0);
-        }
-      }
-      if (HAS_AUX_IN) {
-        if (active) {
-          mbar_wait(&aux_full[grp], aux_phase);
-          aux_phase ^= 1;
-        }
-      } else {
-        bar_sync(bar_id, 128);
-      }
-
-      // (2) accumulator -> registers -> staging
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      uint4 held[CG / 8];  // GELU with two outputs: activated values wait here while `pre` is stored
-      if (active) {
-#pragma unroll
-        for (int s = 0; s < CG / 32; ++s) {
-          const int col_in_tile = grp * CG + s * 32;
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_off + acc * BN + col_in_tile, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = n0 + col_in_tile + q * 8;
-            const bool col_ok = col < p.N;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
-            if (OUT_F32) {
-              if (p.mask != nullptr && col_ok && row < p.M) {
-                const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + row * p.ldd + col);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (((mk.x >> (8 * j)) & 0xFF) == 0) v[j] = 0.f;
-                  if (((mk.y >> (8 * j)) & 0xFF) == 0) v[4 + j] = 0.f;
-                }
-              }
-              *reinterpret_cast<float4*>(stg + stg_off<ROWB>(r_tile, 2 * q)) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(stg + stg_off<ROWB>(r_tile, 2 * q + 1)) = make_float4(v[4], v[5], v[6], v[7]);
-              continue;
-            }
-            const int ch = s * 4 + q;  // 16-byte chunk of the staging row
-            uint8_t* slot = stg + stg_off<ROWB>(r_tile, ch);
-            if (EPI == MH_EPI_BF16 || EPI == MH_EPI_GELU || EPI == MH_EPI_RES) {
-              if (p.bias != nullptr && col_ok) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-            }
-            if (EPI == MH_EPI_GELU) {
-              // the reference evaluates GELU in fp32 on the half-precision fc1 output
-              // (fairseq_code/gelu.py:35 under autocast): round first, then activate.
-              const uint4 pre = f32_to_bf16x8(v);
-              if (p.has_aux_out) *reinterpret_cast<uint4*>(slot) = pre;
-              bf16x8_to_f32(pre, v);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-            }
-            if (EPI == MH_EPI_DGELU) {
-              float pre[8];
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), pre);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
-            }
-            if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
-              if (p.drop.thresh != 0)
-                drop_apply8(p.drop, static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + (col >> 3), v);
-            }
-            if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
-              float a[8];
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), a);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += a[j];
-            }
-            const uint4 o = f32_to_bf16x8(v);
-            if (EPI == MH_EPI_GELU && p.has_aux_out) held[ch] = o;
-            else *reinterpret_cast<uint4*>(slot) = o;
-          }
-        }
-      }
-      // (3) TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      epilogue_tile<BN, EPI>(p, &tmD, &tmAuxIn, &tmAuxOut, e, tmem_base + acc * BN, m0, n0, has_k, &tfull[acc], acc_phase,
+                             &aux_full[e.grp], aux_phase, smem_u32(&tempty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-
-      // (4) staging -> global
-      if (active) {
-        fence_proxy_async_smem();
-        bar_sync(bar_id, 128);
-        if (EPI == MH_EPI_GELU && p.has_aux_out) {
-          if (leader) {
-            tma_store_2d(&tmAuxOut, stg, gcol0, m0);
-            bulk_commit();
-            bulk_wait_read0();
-          }
-          bar_sync(bar_id, 128);
-#pragma unroll
-          for (int ch = 0; ch < CG / 8; ++ch) *reinterpret_cast<uint4*>(stg + stg_off<ROWB>(r_tile, ch)) = held[ch];
-          fence_proxy_async_smem();
-          bar_sync(bar_id, 128);
-        }
-        if (leader) {
-          if (OUT_F32) tma_reduce_add_2d(&tmD, stg, gcol0, m0);
-          else tma_store_2d(&tmD, stg, gcol0, m0);
-          bulk_commit();
-        }
-      }
     }
-    if (leader) bulk_wait0();
+    if (e.leader) bulk_wait0();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.  Each CTA loads
+// its own 128 rows of A and HALF of the B tile (128 of the 256 columns); the leader CTA issues one
+// 256 x 256 x 16 MMA per k-step that reads both CTAs' shared memory and writes 128 accumulator rows into
+// each CTA's TMEM.  Per SM this halves the B-operand shared-memory traffic (the 1-CTA kernel sits at the
+// 128 B/clk shared-memory roof once the epilogue staging traffic is added) and the smaller stage (32 KB)
+// buys a 5-deep ring.  Each CTA runs the normal epilogue on its own 128 rows.
+//   full[s]   : leader's barrier; both CTAs' TMA loads complete_tx on it (peer bit cleared in the address)
+//   empty[s]  : one per CTA; released by a multicast tcgen05.commit
+//   tfull[a]  : one per CTA (multicast commit);  tempty[a]: leader's, 2 x 16 warp arrivals (remote for the peer)
+// ---------------------------------------------------------------------------------------------
+constexpr int G2_BN = 256;
+constexpr int G2_STAGES = 5;
+constexpr int G2_A_BYTES = BM * BK * 2;          // this CTA's 128 rows of A
+constexpr int G2_B_BYTES = (G2_BN / 2) * BK * 2; // this CTA's half of the B tile
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + EPI_GROUPS * STG_CHUNK + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+template <int EPI, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
+                 const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
+  constexpr int BN = G2_BN;
+  extern __shared__ uint8_t smem_raw[];
+  // identical offsets in both CTAs (the dynamic smem base is the same for every CTA of a launch)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + G2_STAGES * G2_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_GROUPS * STG_CHUNK);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + G2_STAGES;
+  uint64_t* tfull = bars + 2 * G2_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* aux_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + EPI_GROUPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2 * EPI_WARPS);
+    }
+    for (int s = 0; s < EPI_GROUPS; ++s) mbar_init(&aux_full[s], 1);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (p.N + BN - 1) / BN;
+  const int kblocks_total = (p.K + BK - 1) / BK;
+  const int splits = p.split_k;
+  const int kb_per_split = (kblocks_total + splits - 1) / splits;
+  const int num_tiles = num_m2 * num_n * splits;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == PRODUCER_WARP) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int split = tile % splits;
+        const int mn = tile / splits;
+        const int m0 = (mn / num_n) * (2 * BM) + rank * BM;
+        const int n0 = (mn % num_n) * BN + rank * (BN / 2);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kblocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t fb = smem_u32(&full[stage]) & PEER_MASK;  // the leader's barrier
+          if (is_leader) mbar_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
+          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+          uint8_t* sb = sa + G2_A_BYTES;
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * (BK * 128), &tmA, fb, m0 + c * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, fb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) tma_load_2d_pair(sb + c * (BK * 128), &tmB, fb, n0 + c * 64, kb * BK);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (is_leader && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int split = tile % splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kblocks_total, kb0 + kb_per_split);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint32_t sb = sa + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_sdesc(sa + k * 2048, BK * 128, 1024) : make_sdesc(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? make_sdesc(sb + k * 2048, BK * 128, 1024) : make_sdesc(sb + k * 32, 0, 1024);
+            umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty[stage]);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const EpiThread e = make_epi_thread(warp, lane, staging);
+    int acc = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int mn = tile / splits;
+      const int m0 = (mn / num_n) * (2 * BM) + rank * BM, n0 = (mn % num_n) * BN;
+      const int kb0 = (tile % splits) * kb_per_split;
+      const bool has_k = kb0 < kblocks_total;
+      epilogue_tile<BN, EPI>(p, &tmD, &tmAuxIn, &tmAuxOut, e, tmem_base + acc * BN, m0, n0, has_k, &tfull[acc], acc_phase,
+                             &aux_full[e.grp], aux_phase, smem_u32(&tempty[acc]) & PEER_MASK);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (e.leader) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's shared memory / barriers must stay alive until both CTAs are done
+  if (warp == MMA_WARP)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -412,6 +677,47 @@ static int launch(const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st
   return 0;
 }
 
+template <int EPI, bool A_MN, bool B_MN>
+static int launch_pair(const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
+  auto kfn = gemm_pair_kernel<EPI, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    configured = true;
+  }
+  kfn<<<grid, GEMM_THREADS, G2_SMEM, st>>>(t.a, t.b, t.d, t.aux_in, t.aux_out, d);
+  MH_LAUNCH_CHECK();
+  ++g_launches;
+  return 0;
+}
+
+template <int EPI>
+static int dispatch_major_pair(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
+  if (!a->a_mn && !a->b_mn) return launch_pair<EPI, false, false>(t, d, grid, st);
+  if constexpr (EPI == MH_EPI_BF16 || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_F32) {
+    if (!a->a_mn && a->b_mn) return launch_pair<EPI, false, true>(t, d, grid, st);
+  }
+  if constexpr (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
+    if (a->a_mn && a->b_mn) return launch_pair<EPI, true, true>(t, d, grid, st);
+    if (a->a_mn && !a->b_mn) return launch_pair<EPI, true, false>(t, d, grid, st);
+  }
+  set_error("operand layout a_mn=%d b_mn=%d is not built for epilogue %d", a->a_mn, a->b_mn, a->epilogue);
+  return 1;
+}
+
+static int dispatch_epi_pair(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
+  switch (a->epilogue) {
+    case MH_EPI_BF16: return dispatch_major_pair<MH_EPI_BF16>(a, t, d, grid, st);
+    case MH_EPI_GELU: return dispatch_major_pair<MH_EPI_GELU>(a, t, d, grid, st);
+    case MH_EPI_RES: return dispatch_major_pair<MH_EPI_RES>(a, t, d, grid, st);
+    case MH_EPI_F32: return dispatch_major_pair<MH_EPI_F32>(a, t, d, grid, st);
+    case MH_EPI_DGELU: return dispatch_major_pair<MH_EPI_DGELU>(a, t, d, grid, st);
+    case MH_EPI_ADD: return dispatch_major_pair<MH_EPI_ADD>(a, t, d, grid, st);
+  }
+  set_error("unknown epilogue %d", a->epilogue);
+  return 1;
+}
+
 template <int BN, int EPI>
 static int dispatch_major(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
   if constexpr (EPI == MH_EPI_F32 && BN != 128) {
@@ -465,20 +771,36 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   const int es = out_f32 ? 4 : 2;
   MH_CHECK((a->ldd * es) % 16 == 0, "D row pitch must be a multiple of 16 bytes");
   const int num_m = (a->M + BM - 1) / BM;
-  int bn = a->block_n;
-  if (out_f32) {
-    MH_CHECK(bn == 0 || bn == 128, "fp32 accumulate epilogue needs block_n = 128");
-    bn = 128;
-  }
-  if (bn == 0) bn = (a->N >= 256 && num_m * ((a->N + 255) / 256) >= sms) ? 256 : 128;
-  MH_CHECK(bn == 128 || bn == 256, "block_n must be 128 or 256");
-  const int num_n = (a->N + bn - 1) / bn;
   const int kblocks = (a->K + BK - 1) / BK;
+  // tile shape: block_n 0 = auto, 128 / 256 = single-CTA 128 x block_n tiles, -256 = CTA-pair 256 x 256 tiles
+  int bn = a->block_n;
+  static const bool pair_allowed = [] { const char* e = getenv("MH_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  bool pair = false;
+  if (bn == -256) {
+    pair = true;
+  } else if (bn == 0 && pair_allowed && a->M >= 2 * BM && a->N >= 128) {
+    // big GEMMs: the pair kernel whenever its 256 x 256 tiles (x split-K for wgrad) can occupy the SM pairs
+    const int pt = ((a->M + 255) / 256) * ((a->N + 255) / 256);
+    pair = out_f32 ? true : pt >= sms / 2;
+  }
+  if (!pair) {
+    if (out_f32) {
+      MH_CHECK(bn == 0 || bn == 128, "fp32 accumulate epilogue: block_n must be 0, 128 or -256");
+      bn = 128;
+    }
+    if (bn == 0) bn = (a->N >= 256 && num_m * ((a->N + 255) / 256) >= sms) ? 256 : 128;
+    MH_CHECK(bn == 128 || bn == 256, "block_n must be 0, 128, 256 or -256");
+  } else {
+    bn = G2_BN;
+  }
+  const int tiles_m = pair ? (a->M + 2 * BM - 1) / (2 * BM) : num_m;
+  const int num_n = (a->N + bn - 1) / bn;
+  const int units = pair ? sms / 2 : sms;  // CTAs or CTA pairs that can be resident
   int splits = 1;
   if (out_f32) {
     splits = a->split_k;
     if (splits <= 0) {
-      splits = sms / (num_m * num_n);
+      splits = units / (tiles_m * num_n);
       if (splits < 1) splits = 1;
       if (splits > kblocks / 4) splits = kblocks / 4 > 0 ? kblocks / 4 : 1;  // keep >= 4 k-blocks per split
       if (splits > 32) splits = 32;
@@ -491,14 +813,15 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
 
   GemmMaps t;
   int rc;
+  const int b_rows = pair ? bn / 2 : bn;  // B rows (K-major) each CTA loads per stage
   if (!a->a_mn) rc = make_tmap_2d(&t.a, a->A, a->M, a->K, a->lda, BK, BM);
   else rc = make_tmap_2d(&t.a, a->A, a->K, a->M, a->lda, 64, BK);
   if (rc) return rc;
-  if (!a->b_mn) rc = make_tmap_2d(&t.b, a->B, a->N, a->K, a->ldb, BK, bn);
+  if (!a->b_mn) rc = make_tmap_2d(&t.b, a->B, a->N, a->K, a->ldb, BK, b_rows);
   else rc = make_tmap_2d(&t.b, a->B, a->K, a->N, a->ldb, 64, BK);
   if (rc) return rc;
-  // epilogue tiles: one box of 128 rows x (bn / 4) columns per column group
-  const int cg = bn / EPI_GROUPS;
+  // epilogue tiles: one box of 128 rows x (bn / 4) columns per column group (fp32: 32-column passes)
+  const int cg = out_f32 ? 32 : bn / EPI_GROUPS;
   const int rowb = cg * es;
   rc = make_tmap_2d(&t.d, a->D, a->M, a->N, a->ldd, cg, BM, es, rowb);
   if (rc) return rc;
@@ -521,7 +844,8 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   d.mask = a->mask;
   d.drop = make_drop(a->p_drop, a->seed, a->site);
   d.split_k = splits;
-  const int tiles = num_m * num_n * splits;
+  const int tiles = tiles_m * num_n * splits;
+  if (pair) return dispatch_epi_pair(a, t, d, 2 * (tiles < units ? tiles : units), st);
   const int grid = tiles < sms ? tiles : sms;
   if (bn == 256) return dispatch_epi<256>(a, t, d, grid, st);
   return dispatch_epi<128>(a, t, d, grid, st);

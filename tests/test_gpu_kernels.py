@@ -50,6 +50,13 @@ def _seed():
     (300, 768, 1536, False, True, 0),        # dgrad through a row-pruned fc1 (B MN-major)
     (256, 256, 256, True, False, 256),
     (256, 256, 256, True, True, 128),
+    # CTA-pair (cta_group::2) 256 x 256 tiles, every operand layout, ragged M / N edges
+    (256, 256, 64, False, False, -256),
+    (3000, 2304, 768, False, False, -256),
+    (1000, 704, 768, False, False, -256),
+    (300, 768, 1536, False, True, -256),
+    (512, 512, 256, True, False, -256),
+    (776, 328, 192, True, True, -256),
 ])
 def test_gemm_bf16_matches_fp32(M, N, Kd, a_mn, b_mn, bn):
     k = K()
@@ -63,9 +70,10 @@ def test_gemm_bf16_matches_fp32(M, N, Kd, a_mn, b_mn, bn):
     assert rel(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("M,N,Kd,split", [(768, 3072, 3000, 0), (768, 768, 3000, 0), (2304, 768, 24000, 0), (512, 80, 3000, 3),
-                                          (768, 1536, 1454, 5)])
-def test_gemm_wgrad_f32_accumulates_with_mask(M, N, Kd, split):
+@pytest.mark.parametrize("M,N,Kd,split,bn", [(768, 3072, 3000, 0, 0), (768, 768, 3000, 0, 0), (2304, 768, 24000, 0, 0),
+                                             (512, 80, 3000, 3, 0), (768, 1536, 1454, 5, 0), (768, 3072, 3000, 0, 128),
+                                             (704, 776, 1000, 2, -256)])
+def test_gemm_wgrad_f32_accumulates_with_mask(M, N, Kd, split, bn):
     """dW += dY^T X with both operands MN-major, fp32 red.add epilogue, optional prune mask,
     split-K; checks the accumulate-into-existing-gradient semantics too."""
     k = K()
@@ -75,7 +83,7 @@ def test_gemm_wgrad_f32_accumulates_with_mask(M, N, Kd, split):
     prev = torch.randn(M, N, device=DEV)
     ref = dy.float().t() @ x.float()
     out = prev.clone()
-    k.gemm(dy, x, out, a_mn=True, b_mn=True, epilogue=k.EPI_F32, mask=mask, split_k=split)
+    k.gemm(dy, x, out, a_mn=True, b_mn=True, epilogue=k.EPI_F32, mask=mask, split_k=split, block_n=bn)
     want = prev + ref * mask
     assert rel(out, want) < 1e-4
     assert torch.equal(out[~mask], prev[~mask]), "masked-out gradient entries must be untouched"

@@ -95,3 +95,17 @@ if which in ("all", "epi"):
     timeit(lambda: K.gemm(y, u, g2, a_mn=True, b_mn=True, epilogue=K.EPI_F32), f1, "fc2 wgrad f32")
     mk = torch.rand(3072, 768, device=dev) > 0.5
     timeit(lambda: K.gemm(u, x, g1, a_mn=True, b_mn=True, epilogue=K.EPI_F32, mask=mk), f1, "fc1 wgrad f32 masked")
+if which in ("bn",):
+    for (M, N, Kd) in [(24000, 2304, 768), (24000, 3072, 768), (24000, 768, 3072), (24000, 768, 768)]:
+        a = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
+        b = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for bn in (128, 256):
+            fn = lambda: K.gemm(a, b, out, block_n=bn)
+            for _ in range(3): fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20): fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"bn={bn} M={M} N={N} K={Kd}: {ms*1e3:.1f} us  {2*M*N*Kd/ms/1e9:.1f} TFLOP/s", flush=True)

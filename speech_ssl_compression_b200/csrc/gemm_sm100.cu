@@ -165,16 +165,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
     return;
   }
 
-  uint4 held[CG / 8];  // GELU with two outputs: activated values wait here while `pre` is stored
+  // GELU with two outputs: activated values wait in registers while `pre` is stored.  The 32-column
+  // sub-chunk loop stays rolled (the unrolled 64-column body was ~30 KB of SASS per kernel and fetch-bound
+  // like the attention loops), so the held values live in two explicitly named register sets.
+  uint4 held0[4], held1[4];
   // dropout stream position of this thread's row (element (row, col) lives in group row * N/8 + col/8)
   const uint64_t drop_base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + static_cast<uint64_t>(n0 >> 3);
   if (active) {
-#pragma unroll
-    for (int s = 0; s < CG / 32; ++s) {
+    auto sub_chunk = [&](int s) {
       const int col_in_tile = e.grp * CG + s * 32;
       uint32_t r[32];
       tmem_ld32(tmem_acc + e.lane_off + col_in_tile, r);
       tmem_ld_wait();
+      uint4 o4[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int col = n0 + col_in_tile + q * 8;
@@ -216,10 +219,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] += a[j];
         }
-        const uint4 o = f32_to_bf16x8(v);
-        if (EPI == MH_EPI_GELU && p.has_aux_out) held[ch] = o;
-        else *reinterpret_cast<uint4*>(slot) = o;
+        o4[q] = f32_to_bf16x8(v);
+        if (!(EPI == MH_EPI_GELU && p.has_aux_out)) *reinterpret_cast<uint4*>(slot) = o4[q];
       }
+      if (EPI == MH_EPI_GELU && p.has_aux_out) {
+        if (s == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) held0[q] = o4[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) held1[q] = o4[q];
+        }
+      }
+    };
+    if (EPI == MH_EPI_GELU || EPI == MH_EPI_DGELU) {
+      // heavy epilogues: rolled (measured 146 -> 132 us for fc1 + GELU + dropout)
+#pragma unroll 1
+      for (int s = 0; s < CG / 32; ++s) sub_chunk(s);
+    } else {
+      // light epilogues: unrolled (the loop overhead costs more than the extra code)
+#pragma unroll
+      for (int s = 0; s < CG / 32; ++s) sub_chunk(s);
     }
   }
   // (3) TMEM buffer back to the MMA warp
@@ -239,7 +259,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       }
       bar_sync(e.bar_id, 128);
 #pragma unroll
-      for (int ch = 0; ch < CG / 8; ++ch) *reinterpret_cast<uint4*>(stg + stg_off<ROWB>(e.r_tile, ch)) = held[ch];
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + stg_off<ROWB>(e.r_tile, q)) = held0[q];
+      if (CG > 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + stg_off<ROWB>(e.r_tile, 4 + q)) = held1[q];
+      }
       fence_proxy_async_smem();
       bar_sync(e.bar_id, 128);
     }

@@ -180,7 +180,7 @@ def workload_config(args, per_gpu_batch=None):
                         f"(reference: 4 utterances x 8 accumulation micro-batches per optimizer step), dropout 0.1",
             "per_gpu_batch": B, "frames": args.frames, "global_batch": B * args.gpus, "parallelism": f"dp{args.gpus}",
             "l2": "per-step working set (several GB of activations) >> 126 MB L2, no flush needed",
-            "cuda_graph": (not args.no_graph) and args.gpus == 1}
+            "cuda_graph": not args.no_graph}
 
 
 def live_gemm_roofline(ts, batch, peaks):
@@ -336,6 +336,8 @@ def main():
     roof = live_gemm_roofline(ts, batches[0], peaks)  # every rank runs it: the step contains collectives
     if rank != 0:
         dist.barrier()
+        if not ts.use_graph:
+            dist.destroy_process_group()
         return
     frames = B * T * world
     value = frames / (ms_resident / 1e3)
@@ -372,9 +374,12 @@ def main():
                                          f"(oracle port of the reference training step)"}
     else:
         out["cpu_baseline"] = None
+    out["config"]["cuda_graph"] = bool(ts.use_graph)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        if not ts.use_graph:  # a captured graph still references the communicator: let process exit release it
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

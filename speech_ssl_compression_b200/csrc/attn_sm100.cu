@@ -44,6 +44,20 @@ struct AttnParams {
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
 __device__ __forceinline__ uint32_t swz(int r, int ch) { return r * 128 + ((ch ^ (r & 7)) << 4); }
 
+// rare path of the forward softmax (lazy rescaling): kept out of line so the hot loop stays small
+__device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
+#pragma unroll 1
+  for (int c = 0; c < HD / 32; ++c) {
+    uint32_t rr[32];
+    tmem_ld32(tmem_o_lane + c * 32, rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * alpha);
+    tmem_st32(tmem_o_lane + c * 32, rr);
+  }
+  tmem_st_wait();
+}
+
 constexpr int FWD_SMEM = TILE_BYTES * (1 + 2 + 2 + 2) + 128;  // 2 CTAs / SM: <= 115,712 B each
 
 __global__ void __launch_bounds__(192, 2)
@@ -155,88 +169,91 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tc_fence_after();
       int lim = kv_len - k0;                       // keys [0, lim) of this block are visible
       if (p.causal) lim = min(lim, q - k0 + 1);
-      const bool full = __all_sync(0xffffffffu, lim >= BKV);
-      // ---- pass 1: row maximum.  Loops are kept rolled (one 32-column chunk per trip): the fully unrolled
-      // body was ~58 KB of SASS, far beyond the instruction caches, and ran slower than this compact form.
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_s + lane_off + c * 32, rr);
-        tmem_ld_wait();
-        if (full) {
-          // four independent chains instead of one 32-deep dependent FMNMX chain
-          float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              m4[u] = fmaxf(m4[u], fmaxf(__uint_as_float(rr[i + 2 * u]), __uint_as_float(rr[i + 2 * u + 1])));
-          }
-          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < lim) mx = fmaxf(mx, __uint_as_float(rr[i]));
-        }
-      }
-      const float m_blk = mx * sc;
+      // ---- reference maximum.  TMEM -> register bandwidth is the scarce resource of this kernel, so the
+      // score tile is read ONCE per block where possible: only the first block runs a separate max pass; later
+      // blocks exponentiate against the running reference m_run and track their own maximum on the fly.
+      // Any reference gives the exact softmax as long as nothing overflows (bf16 P and fp32 sums share the
+      // fp32 exponent range), so the reference is only raised -- O and l rescaled, the block redone -- when
+      // a block exceeds it by more than 2^64 (practically never; the path exists for correctness).
       if (j == 0) {
-        m_run = m_blk;
-      } else {
-        const bool need = m_blk > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          // rescale this warp's rows of O (PV_{j-1} must have landed first)
-          const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;
-          mbar_wait(o_full, (j - 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t rr[32];
-            tmem_ld32(tmem_o + lane_off + c * 32, rr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * alpha);
-            tmem_st32(tmem_o + lane_off + c * 32, rr);
-          }
-          tmem_st_wait();
-          l_run *= alpha;
-          if (need) m_run = m_blk;
-        }
-      }
-      const float m_off = (m_run == -INFINITY ? 0.f : m_run) - lg_scale;
-      // ---- pass 2: probabilities, row sum, dropout, bf16 P into swizzled smem
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint64_t drop_base = row_id * groups_per_row + static_cast<uint64_t>(k0 >> 3);
-      // one 32-key chunk per trip (4 groups of 8 unrolled inside): measured best trade between instruction
-      // level parallelism and code size (the fully unrolled 128-key body ran 25 % slower on instruction fetch,
-      // an 8-key rolled body 15 % slower on loop overhead)
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_s + lane_off + c * 32, rr);
-        tmem_ld_wait();
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_s + lane_off + c * 32, rr);
+          tmem_ld_wait();
+          const int rem32 = lim - c * 32;
+          if (rem32 >= 32) {
+            float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
+            for (int i = 0; i < 32; i += 8) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_off));
-          const int rem = lim - (c * 32 + g * 8);  // visible keys left in this group (only the last block has < 8)
-          if (rem < 8) {
+              for (int u = 0; u < 4; ++u)
+                m4[u] = fmaxf(m4[u], fmaxf(__uint_as_float(rr[i + 2 * u]), __uint_as_float(rr[i + 2 * u + 1])));
+            }
+            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = i < rem ? pv[i] : 0.f;
+            for (int i = 0; i < 32; ++i)
+              if (i < rem32) mx = fmaxf(mx, __uint_as_float(rr[i]));
           }
-          // pairwise tree + four accumulators: no long dependent FADD chain
-          l4[g] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
-          if (use_drop) {
-            const uint4 bits = ds.bits(drop_base + (c * 4 + g));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = ds.keep(bits, i) ? pv[i] : 0.f;
-          }
-          const int kc = c * 32 + g * 8;  // key column inside the block
-          uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
-          *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
         }
+        m_run = mx * sc;
+      }
+      // ---- probabilities, row sum, dropout, bf16 P into swizzled smem
+      float l4[4];
+      const uint64_t drop_base = row_id * groups_per_row + static_cast<uint64_t>(k0 >> 3);
+#pragma unroll 1
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const float m_off = (m_run == -INFINITY ? 0.f : m_run) - lg_scale;
+        float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        l4[0] = l4[1] = l4[2] = l4[3] = 0.f;
+        // one 32-key chunk per trip (4 groups of 8 unrolled inside): measured best trade between instruction
+        // level parallelism and code size (the fully unrolled 128-key body was fetch-bound, 25 % slower)
+#pragma unroll 1
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_s + lane_off + c * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int rem = lim - (c * 32 + g * 8);  // visible keys left in this group (only the last block has < 8)
+            if (rem < 8) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i >= rem) rr[g * 8 + i] = 0xff800000u;  // -inf: probability 0, ignored by the maximum
+            }
+            float pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_off));
+            b4[g] = fmaxf(b4[g], fmaxf(fmaxf(fmaxf(__uint_as_float(rr[g * 8]), __uint_as_float(rr[g * 8 + 1])),
+                                             fmaxf(__uint_as_float(rr[g * 8 + 2]), __uint_as_float(rr[g * 8 + 3]))),
+                                       fmaxf(fmaxf(__uint_as_float(rr[g * 8 + 4]), __uint_as_float(rr[g * 8 + 5])),
+                                             fmaxf(__uint_as_float(rr[g * 8 + 6]), __uint_as_float(rr[g * 8 + 7])))));
+            // pairwise tree + four accumulators: no long dependent FADD chain
+            l4[g] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+            if (use_drop) {
+              const uint4 bits = ds.bits(drop_base + (c * 4 + g));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pv[i] = ds.keep(bits, i) ? pv[i] : 0.f;
+            }
+            const int kc = c * 32 + g * 8;  // key column inside the block
+            uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
+            *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
+          }
+        }
+        const float m_blk = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3])) * sc;
+        const bool need = m_blk > m_run + 64.0f;  // (false for m_blk = -inf and for attempt 1)
+        if (!__any_sync(0xffffffffu, need)) break;
+        // rare: raise the reference of the offending rows, rescale their O / l, redo the block
+        const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;  // m_run = -inf -> 0
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);  // PV_{j-1} must have landed before O is touched
+          tc_fence_after();
+          rescale_o_rows(tmem_o + lane_off, alpha);
+        }
+        l_run *= alpha;
+        if (need) m_run = m_blk;
       }
       l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_proxy_async_smem();

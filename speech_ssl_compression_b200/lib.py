@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmh_b200.so")
+LIB_PATH = os.environ.get("MH_B200_LIB") or os.path.join(_HERE, "libmh_b200.so")  # override: A/B builds of the same ABI
 
 EPI_BF16, EPI_GELU, EPI_RES, EPI_F32, EPI_DGELU, EPI_ADD = range(6)
 

@@ -77,8 +77,14 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 // LN output).  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).
 // Also emits dx_drop = dx * keep mask of `dout` (the dropout that sat on the GEMM output
 // feeding this LayerNorm's input) so the dgrad/wgrad GEMMs can consume it directly.
+#ifndef LN_BWD_MINB
+#define LN_BWD_MINB 2
+#endif
+#ifndef LN_BWD_GRID_MULT
+#define LN_BWD_GRID_MULT 2
+#endif
 template <int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, LN_BWD_MINB)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma,
@@ -231,7 +237,7 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
                                 uint64_t seed_out, uint32_t site_out, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm_bwd: bad shape %d x %d", rows, cols);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * 2);
+  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_BWD_GRID_MULT);
   const DropCfg din = make_drop(p_in, seed_in, site_in), dout = make_drop(p_out, seed_out, site_out);
   return dispatch_nch(cols, [&](auto nch) {
     ln_bwd_kernel<decltype(nch)::value><<<grid, LN_WARPS * 32, 0, st>>>(

@@ -110,6 +110,42 @@ def _wgrad(dy, x, lin, col0=0, ncols=None):
             g.add_(tmp * bm)
 
 
+def _wgrad_qkv(dqkv, x, mha, E):
+    """Weight / bias gradients of the q, k, v projections.  When their gradients sit back to back in the flat
+    buffer (trainer.trainable_params) and carry no prune masks: ONE [3E, C] wgrad GEMM and one column sum."""
+    lins = (mha.q_proj, mha.k_proj, mha.v_proj)
+    pw = [param_and_mask(l, "weight") for l in lins]
+    pb = [param_and_mask(l, "bias") for l in lins]
+    fused = all(w.requires_grad and m is None and w.grad is not None for w, m in pw)
+    if fused:
+        g = [w.grad for w, _ in pw]
+        n = g[0].numel()
+        fused = (g[0].is_contiguous() and g[1].data_ptr() == g[0].data_ptr() + 4 * n
+                 and g[2].data_ptr() == g[1].data_ptr() + 4 * n and g[0].shape == g[1].shape == g[2].shape)
+    if not fused:
+        for i, lin in enumerate(lins):
+            _wgrad(dqkv, x, lin, col0=i * E, ncols=E)
+        return
+    C = g[0].shape[1]
+    K.gemm(dqkv, x, torch.as_strided(g[0], (3 * E, C), (C, 1)), a_mn=True, b_mn=True, epilogue=K.EPI_F32)
+    gb = [b.grad if (b is not None and b.requires_grad and m is None) else None for b, m in pb]
+    if all(t is not None for t in gb) and gb[1].data_ptr() == gb[0].data_ptr() + 4 * E \
+            and gb[2].data_ptr() == gb[1].data_ptr() + 4 * E:
+        K.colsum_add(dqkv, torch.as_strided(gb[0], (3 * E,), (1,)))
+    else:
+        for i, lin in enumerate(lins):
+            b, bm = pb[i]
+            if b is not None and b.requires_grad:
+                gi = _grad_of(b)
+                dyv = dqkv[:, i * E:(i + 1) * E]
+                if bm is None:
+                    K.colsum_add(dyv, gi)
+                else:
+                    tmp = torch.zeros_like(gi)
+                    K.colsum_add(dyv, tmp)
+                    gi.add_(tmp * bm)
+
+
 # ---------------------------------------------------------------------------------------------
 # plain linear (pre_extract_proj, final_proj, prediction heads)
 # ---------------------------------------------------------------------------------------------
@@ -328,8 +364,7 @@ class EncoderLayerFn(torch.autograd.Function):
         K.gemm(dz1, wo, dctx, b_mn=True)
         dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, B, T, heads, causal=causal, p_drop=p_att, seed=seed,
                           site=site_base + SITE_ATTN)
-        for i, lin in enumerate((mha.q_proj, mha.k_proj, mha.v_proj)):
-            _wgrad(dqkv, a_in, lin, col0=i * E, ncols=E)
+        _wgrad_qkv(dqkv, a_in, mha, E)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)

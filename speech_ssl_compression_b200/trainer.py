@@ -54,12 +54,32 @@ class FusedAdam:
 
 
 def trainable_params(expert):
-    """Layer-contiguous parameter order (so each encoder layer is one all-reduce bucket)."""
+    """Layer-contiguous parameter order (so each encoder layer is one all-reduce bucket).  Inside an
+    attention module the q, k, v weights (then their biases) are placed back to back in the order of the
+    fused QKV GEMM's columns, so their three weight-gradient GEMMs / bias column sums collapse into one
+    call writing a [3E, C] block of the flat gradient buffer (ops._wgrad_qkv)."""
+    from .fairseq_code import MultiheadAttention
+
+    order = {}
+    for m in expert.modules():
+        if isinstance(m, MultiheadAttention):
+            group = []
+            for name in ("weight", "bias"):
+                for proj in (m.q_proj, m.k_proj, m.v_proj):
+                    t = proj._parameters.get(name + "_orig", proj._parameters.get(name))
+                    if t is not None:
+                        group.append(t)
+            first = min((id(t) for t in group), default=None)
+            for t in group:
+                order[id(t)] = group
     seen, out = set(), []
     for p in expert.parameters():
-        if p.requires_grad and id(p) not in seen:
-            seen.add(id(p))
-            out.append(p)
+        if not p.requires_grad or id(p) in seen:
+            continue
+        for t in order.get(id(p), [p]):  # the first q/k/v tensor met pulls its whole group in, in GEMM order
+            if t.requires_grad and id(t) not in seen:
+                seen.add(id(t))
+                out.append(t)
     return out
 
 

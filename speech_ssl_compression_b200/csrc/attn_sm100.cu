@@ -58,17 +58,28 @@ __device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
   tmem_st_wait();
 }
 
-constexpr int FWD_SMEM = TILE_BYTES * (1 + 2 + 2 + 2) + 128;  // 2 CTAs / SM: <= 115,712 B each
+// Forward key-block size.  64 keys per block: S needs 64 TMEM columns (+ 64 for O = one 128-column allocation)
+// and the CTA 64 KB of shared memory, so THREE independent CTAs share an SM.  Softmax warps of one CTA move in
+// lockstep (they wait on the same MMA barriers); only warps of different CTAs overlap each other's stalls.
+#ifndef MH_FWD_BKV
+#define MH_FWD_BKV 64
+#endif
+constexpr int FBKV = MH_FWD_BKV;
+constexpr int FKV_TILE = FBKV * 128;            // one K or V block: FBKV rows x 128 B
+constexpr int FP_BYTES = BQ * FBKV * 2;         // bf16 P tile
+constexpr int FWD_SMEM = TILE_BYTES + 4 * FKV_TILE + FP_BYTES + 128;
+constexpr int FWD_CTAS_PER_SM = FBKV == 64 ? 3 : 2;
+constexpr int FWD_TMEM_COLS = FBKV == 64 ? 128 : 256;
 
-__global__ void __launch_bounds__(192, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+__global__ void __launch_bounds__(192, FWD_CTAS_PER_SM)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs a 1024-byte aligned base
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
-  uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
-  uint8_t* sP = sV + 2 * TILE_BYTES;   // 2 swizzle atoms (keys 0-63 | 64-127)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+  uint8_t* sV = sK + 2 * FKV_TILE;     // 2 stages
+  uint8_t* sP = sV + 2 * FKV_TILE;     // one 128B-swizzle atom per 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FP_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -83,10 +94,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   const int kv_len = min(p.kv_len ? p.kv_len[b] : p.T, p.T);
   int kv_end = kv_len;
   if (p.causal) kv_end = min(kv_end, q0 + BQ);
-  const int n_kv = (kv_end + BKV - 1) / BKV;
+  const int n_kv = (kv_end + FBKV - 1) / FBKV;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
@@ -94,13 +106,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 5) { tmem_alloc(tmem_slot, FWD_TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // 128 columns
-  const uint32_t tmem_o = tmem_base + 128;  // 64 columns
+  const uint32_t tmem_s = tmem_base;         // FBKV columns
+  const uint32_t tmem_o = tmem_base + FBKV;  // 64 columns
 
   if (warp == 4) {
     if (elect_one()) {
@@ -109,22 +121,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-        tma_load_3d(sK + st * TILE_BYTES, &tm, &kv_full[st], p.E + h * HD, j * BKV, b);
-        tma_load_3d(sV + st * TILE_BYTES, &tm, &kv_full[st], 2 * p.E + h * HD, j * BKV, b);
+        mbar_expect_tx(&kv_full[st], 2 * FKV_TILE);
+        tma_load_3d(sK + st * FKV_TILE, &tmKV, &kv_full[st], p.E + h * HD, j * FBKV, b);
+        tma_load_3d(sV + st * FKV_TILE, &tmKV, &kv_full[st], 2 * p.E + h * HD, j * FBKV, b);
       }
     }
     __syncwarp();
   } else if (warp == 5) {
     if (elect_one()) {
-      const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, false, false);
+      const uint32_t idesc_s = make_idesc_bf16(BQ, FBKV, false, false);
       const uint32_t idesc_o = make_idesc_bf16(BQ, HD, false, true);
       mbar_wait(q_full, 0);
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t a = smem_u32(sQ), bk = smem_u32(sK + st * TILE_BYTES);
+        const uint32_t a = smem_u32(sQ), bk = smem_u32(sK + st * FKV_TILE);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(tmem_s, make_sdesc(a + k * 32, 0, 1024), make_sdesc(bk + k * 32, 0, 1024), idesc_s, k > 0);
@@ -135,11 +147,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         const int st = j & 1;
         mbar_wait(p_full, j & 1);  // P_j in smem, S_j / O_{j-1} consumed
         tc_fence_after();
-        const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + st * TILE_BYTES);
+        const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + st * FKV_TILE);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
+        for (int k = 0; k < FBKV / 16; ++k)
           umma_bf16(tmem_o, make_sdesc(ap + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
-                    make_sdesc(bv + k * 2048, TILE_BYTES, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    make_sdesc(bv + k * 2048, FKV_TILE, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(o_full);
         if (j + 1 < n_kv) issue_s(j + 1);
@@ -164,7 +176,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      const int k0 = j * BKV;
+      const int k0 = j * FBKV;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       int lim = kv_len - k0;                       // keys [0, lim) of this block are visible
@@ -178,7 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       if (j == 0) {
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < BKV / 32; ++c) {
+        for (int c = 0; c < FBKV / 32; ++c) {
           uint32_t rr[32];
           tmem_ld32(tmem_s + lane_off + c * 32, rr);
           tmem_ld_wait();
@@ -211,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         // one 32-key chunk per trip (4 groups of 8 unrolled inside): measured best trade between instruction
         // level parallelism and code size (the fully unrolled 128-key body was fetch-bound, 25 % slower)
 #pragma unroll 1
-        for (int c = 0; c < BKV / 32; ++c) {
+        for (int c = 0; c < FBKV / 32; ++c) {
           uint32_t rr[32];
           tmem_ld32(tmem_s + lane_off + c * 32, rr);
           tmem_ld_wait();
@@ -293,7 +305,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 256);
+  if (warp == 5) tmem_dealloc(tmem_base, FWD_TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------- backward
@@ -642,8 +654,10 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_fwd: bad shape B=%d T=%d heads=%d", B, T, heads);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int E = heads * HD;
-  CUtensorMap tm;
+  CUtensorMap tm, tmkv;
   int rc = make_tmap_3d(&tm, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, BQ);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tmkv, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, FBKV);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -655,7 +669,7 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
   p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop(p_drop, seed, site);
-  attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, p);
+  attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, tmkv, p);
   MH_LAUNCH_CHECK();
   ++g_launches;
   return 0;

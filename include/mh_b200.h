@@ -223,11 +223,13 @@ int mh_col_abs_sums(const float* w, long long ld, double* out, int rows, int col
  * Fused Adam step (runner.py:411-427: grad /= n; clip_grad_norm_; Adam; zero_grad) over a
  * flat fp32 parameter buffer.  sumsq: device scalar holding the global grad sum of squares
  * (from mh_sumsq); clip applied as min(1, max_norm / (sqrt(sumsq)*grad_scale + 1e-6)).
+ * bf16_shadow (optional, same indexing as param): bf16 copy of the updated parameters, written in the same
+ * pass -- the next step's GEMM operands, replacing the per-step casts of runner.py:363's autocast.
  * ------------------------------------------------------------------------------------- */
 int mh_sumsq(const float* x, long long n, float* out, void* stream);
 int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, const unsigned long long* step /* device, 1-based */, float grad_scale,
-                 float max_norm, const float* sumsq, int zero_grad, void* stream);
+                 float max_norm, const float* sumsq, int zero_grad, void* bf16_shadow, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
             float lr, float b1, float b2, float eps, float wd, const unsigned long long* __restrict__ step_ptr, float grad_scale,
-            float max_norm, const float* __restrict__ sumsq, int zero_grad) {
+            float max_norm, const float* __restrict__ sumsq, int zero_grad, __nv_bfloat16* __restrict__ shadow) {
   const float step = static_cast<float>(*step_ptr);
   float clip = 1.f;
   bool skip = false;
@@ -65,6 +65,9 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
       *reinterpret_cast<float4*>(p + i) = pv;
       *reinterpret_cast<float4*>(m + i) = mv;
       *reinterpret_cast<float4*>(v + i) = vv;
+      // bf16 shadow of the updated parameters = next step's GEMM operands (replaces the per-step weight prep)
+      if (shadow != nullptr)
+        *reinterpret_cast<uint2*>(shadow + i) = make_uint2(f32x2_to_bf16(pv.x, pv.y), f32x2_to_bf16(pv.z, pv.w));
     }
     if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -88,14 +91,15 @@ extern "C" int mh_sumsq(const float* x, long long n, float* out, void* stream) {
 
 extern "C" int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                             float beta1, float beta2, float eps, float weight_decay, const unsigned long long* step, float grad_scale,
-                            float max_norm, const float* sumsq, int zero_grad, void* stream) {
+                            float max_norm, const float* sumsq, int zero_grad, void* bf16_shadow, void* stream) {
   MH_CHECK(n % 4 == 0, "adam: flat buffer length must be a multiple of 4 (got %lld)", n);
   if (n == 0) return 0;
   long long g = (n / 4 + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (g > cap) g = cap;
   adam_kernel<<<static_cast<int>(g), 256, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                   step, grad_scale, max_norm, sumsq, zero_grad);
+                                                   step, grad_scale, max_norm, sumsq, zero_grad,
+                                                   reinterpret_cast<__nv_bfloat16*>(bf16_shadow));
   MH_LAUNCH_CHECK();
   ++g_launches;
   return 0;

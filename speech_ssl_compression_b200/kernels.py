@@ -347,9 +347,10 @@ def sumsq_add(x, out):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, weight_decay=0.0, grad_scale=1.0,
-              max_norm=0.0, sumsq=None, zero_grad=True):
+              max_norm=0.0, sumsq=None, zero_grad=True, shadow=None):
     _call("mh_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), c_longlong(param.numel()), _f(lr), _f(beta1),
-          _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq), c_int(int(zero_grad)), _s())
+          _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq), c_int(int(zero_grad)),
+          _p(shadow), _s())
 
 
 def set_dropout_offset(counter):

@@ -48,6 +48,9 @@ def packed_operands(owner, key, linears):
         w, wm = param_and_mask(lin, "weight")
         b, bm = param_and_mask(lin, "bias")
         parts.append((w, wm, b, bm))
+    shadow = _shadow_operands(parts)
+    if shadow is not None:
+        return shadow
     trainable = any(t is not None and t.requires_grad for p in parts for t in p)
     sig = (_EPOCH[0] if trainable else -1, _sig([t for p in parts for t in p]))
     hit = cache.get(key)
@@ -84,6 +87,38 @@ def grad_hook(module_or_params, device):
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return torch.empty(0, device=device, requires_grad=True)
     return None
+
+
+def _shadow_operands(parts):
+    """Fast path for trainable, unmasked weights that live in a FlatBuffers with a bf16 shadow kept current by the
+    fused optimizer (mh_adam_step writes it in its own pass): the GEMM operand is a VIEW of the shadow -- no per-step
+    weight prep.  Needs the tensors of `parts` back to back in the flat buffer (q, k, v are: trainer.trainable_params)."""
+    flat0 = getattr(parts[0][0], "_mh_flat", None)
+    if flat0 is None or flat0[0].flat_bf16 is None:
+        return None
+    fb, off = flat0
+    if getattr(fb, "_shadow_epoch", None) != _EPOCH[0]:
+        # parameters were changed outside the fused optimizer (load_state_dict, broadcast, surgery): re-sync
+        fb.sync_shadow()
+        fb._shadow_epoch = _EPOCH[0]
+    kdim = parts[0][0].shape[1]
+    w_off, b_off = off, None
+    for w, wm, b, bm in parts:
+        fw, fbias = getattr(w, "_mh_flat", None), getattr(b, "_mh_flat", None) if b is not None else None
+        if wm is not None or bm is not None or b is None or fw is None or fbias is None or fw[0] is not fb or fbias[0] is not fb:
+            return None
+        if fw[1] != w_off or w.shape[1] != kdim or w.data_ptr() != fb.flat_param.data_ptr() + 4 * fw[1]:
+            return None  # not adjacent, or the Parameter was re-pointed (surgery) since the buffers were built
+        if b_off is None:
+            b_off = fbias[1]
+        if fbias[1] != b_off or b.data_ptr() != fb.flat_param.data_ptr() + 4 * fbias[1]:
+            return None
+        w_off += w.numel()
+        b_off += b.numel()
+    n_total = sum(p[0].shape[0] for p in parts)
+    wv = torch.as_strided(fb.flat_bf16, (n_total, kdim), (kdim, 1), off)
+    bv = torch.as_strided(fb.flat_param, (n_total,), (1,), parts[0][2]._mh_flat[1])
+    return wv, bv
 
 
 def _grad_of(p):

@@ -46,11 +46,30 @@ class FlatBuffers:
         self.offsets, self.total = offs, total
         self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_bf16 = None  # bf16 shadow of flat_param (GEMM operands), kept current by the fused optimizer
         for p, o in zip(self.params, offs):
             view = self.flat_param[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
             p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+            p._mh_flat = (self, o)  # lets ops.packed_operands find the parameter's slot in the shadow
+
+    def enable_shadow(self):
+        """Allocate and fill the bf16 shadow (CUDA only)."""
+        from . import kernels as K
+
+        from . import ops
+
+        self.flat_bf16 = torch.empty(self.total, device=self.flat_param.device, dtype=torch.bfloat16)
+        self.sync_shadow()
+        self._shadow_epoch = ops._EPOCH[0]
+        return self.flat_bf16
+
+    def sync_shadow(self):
+        from . import kernels as K
+
+        if self.flat_bf16 is not None:
+            K.to_bf16(self.flat_param, self.flat_bf16)
 
     def span(self, params):
         """(start, end) of the contiguous slice covering ``params`` (must be adjacent)."""

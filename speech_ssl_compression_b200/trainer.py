@@ -25,6 +25,7 @@ class FusedAdam:
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), tuple(betas), float(eps), float(weight_decay)
         self.exp_avg = torch.zeros_like(flat.flat_param)
         self.exp_avg_sq = torch.zeros_like(flat.flat_param)
+        self.shadow = flat.enable_shadow() if flat.flat_param.is_cuda else None
         self.step_count = torch.zeros(1, device=flat.flat_param.device, dtype=torch.int64)
         self.sumsq = torch.zeros(1, device=flat.flat_param.device, dtype=torch.float32)
 
@@ -34,8 +35,9 @@ class FusedAdam:
         K.sumsq_add(self.flat.flat_grad, self.sumsq)
         K.adam_step(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
                     lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
-                    grad_scale=grad_scale, max_norm=max_norm, sumsq=self.sumsq, zero_grad=True)
-        ops.bump_weight_epoch()
+                    grad_scale=grad_scale, max_norm=max_norm, sumsq=self.sumsq, zero_grad=True, shadow=self.shadow)
+        ops.bump_weight_epoch()  # operands that are NOT views of the shadow (pruned / masked weights) are rebuilt
+        self.flat._shadow_epoch = ops._EPOCH[0]  # ... the shadow itself is current
 
     def grad_norm(self, grad_scale=1.0):
         return float(self.sumsq.sqrt().item()) * grad_scale
@@ -107,6 +109,7 @@ class TrainStep:
         self.dp = getattr(expert, "dp", None)
         if self.dp is not None:
             self.dp.attach(self.flat)
+            self.flat.sync_shadow()  # attach() broadcast rank 0's parameters
             if self.dp.enabled and use_graph and os.environ.get("MH_DP_GRAPH", "0") != "1":
                 # NCCL collectives on a side stream inside a captured autograd backward trip stream-capture
                 # isolation in torch 2.11; data-parallel steps run eagerly (the step is GPU-bound either way)

@@ -74,12 +74,15 @@ int mh_gemm(const mh_gemm_args* args, void* stream);
  *   out : bf16 [B*T, E]      lse : f32 [B, heads, T] (base-2 log-sum-exp of the scaled scores)
  *   dropout on the probabilities regenerated from (seed, site) in the backward.
  * ------------------------------------------------------------------------------------- */
-int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, int B, int T, int heads,
+int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, uint8_t* keep_bits, int B, int T, int heads,
                 int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
-/* dqkv : bf16 [B*T, 3*E];  delta : f32 scratch [B, heads, T];  dq_acc : f32 scratch [B*T, E] */
+/* keep_bits : u8 [B, heads, T, 16 * ceil(T / 128)] -- the dropout decisions of the forward (bit i of byte g of a
+ *   query row = key 8 g + i), written by mh_attn_fwd when non-NULL and p_drop > 0 and REQUIRED by mh_attn_bwd when
+ *   p_drop > 0 (1 bit per score instead of re-running Philox in the instruction-bound backward).
+ * dqkv : bf16 [B*T, 3*E];  delta : f32 scratch [B, heads, T];  dq_acc : f32 scratch [B*T, E] */
 int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
-                float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal, float p_drop,
-                uint64_t seed, uint32_t site, void* stream);
+                const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
+                float p_drop, uint64_t seed, uint32_t site, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNorm family (module.py:121-123,129-131,232-236: dropout -> +residual -> LayerNorm is

@@ -39,6 +39,8 @@ struct AttnParams {
   int causal;
   float scale_log2;     // (1/sqrt(64)) * log2(e)
   DropCfg drop;
+  uint8_t* keep;        // optional [B, H, T, keep_pitch]: dropout keep bits (bit i of byte g = key 8g + i), for the backward
+  int keep_pitch;
 };
 
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
@@ -214,6 +216,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
       }
       // ---- probabilities, row sum, dropout, bf16 P into swizzled smem
       float l4[4];
+      // keep bits of this row's keys (saved for the backward: 1 bit per score instead of a second Philox pass)
+      uint8_t* const keep_row = (use_drop && p.keep != nullptr && q < p.T) ? p.keep + row_id * p.keep_pitch + (k0 >> 3) : nullptr;
       const uint64_t drop_base = row_id * groups_per_row + static_cast<uint64_t>(k0 >> 3);
 #pragma unroll 1
       for (int attempt = 0; attempt < 2; ++attempt) {
@@ -227,6 +231,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
           uint32_t rr[32];
           tmem_ld32(tmem_s + lane_off + c * 32, rr);
           tmem_ld_wait();
+          uint32_t kw = 0u;  // keep bits of the 32 keys of this chunk
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int rem = lim - (c * 32 + g * 8);  // visible keys left in this group (only the last block has < 8)
@@ -246,13 +251,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
             l4[g] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
             if (use_drop) {
               const uint4 bits = ds.bits(drop_base + (c * 4 + g));
+              uint32_t kb = 0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pv[i] = ds.keep(bits, i) ? pv[i] : 0.f;
+              for (int i = 0; i < 8; ++i) {
+                const bool k = ds.keep(bits, i);
+                pv[i] = k ? pv[i] : 0.f;
+                kb |= static_cast<uint32_t>(k) << i;
+              }
+              kw |= kb << (8 * g);
             }
             const int kc = c * 32 + g * 8;  // key column inside the block
             uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
             *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
           }
+          if (keep_row != nullptr) reinterpret_cast<uint32_t*>(keep_row)[c] = kw;
         }
         const float m_blk = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3])) * sc;
         const bool need = m_blk > m_run + 64.0f;  // (false for m_blk = -inf and for attempt 1)
@@ -347,6 +359,8 @@ struct AttnBwdParams {
   int causal;
   float scale, scale_log2;
   DropCfg drop;
+  const uint8_t* keep;  // [B, H, T, keep_pitch] keep bits written by the forward (required when dropout is on)
+  int keep_pitch;
 };
 
 // smem: K, V (16 KB each) | Q[2], dO[2] (64 KB) | P (32 KB) | dS (32 KB) | dQ staging 2 x [128 x 64] f32 (64 KB)
@@ -477,11 +491,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int quad = warp & 3, part = warp >> 2;
       const int r = quad * 32 + lane;
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const uint64_t groups_per_row = (p.T + 7) >> 3;
       const int n_iter = n_q - i_begin;
       const int kc0 = part * 32;
       const bool use_drop = p.drop.thresh != 0;
-      const DropState dst8(p.drop);
       // keep-scale s = 1/(1-p) folded into the exponent: pr' = s * P.  With u = keep ? dP : 0:
       //   P_drop = keep ? pr' : 0,   dS = P (s u - delta) c = pr' c (u - delta / s)
       const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
@@ -489,9 +501,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const long long srow0 = (static_cast<long long>(b) * p.H + h) * p.T;
       // per-row statistics of the next query block are fetched one iteration ahead
       float lse_nx = INFINITY, dl_nx = 0.f;
+      uint32_t kb_nx = 0;  // keep bits of this thread's 32 keys for the next query row
+      const uint8_t* keep_col = use_drop ? p.keep + ((k0 + kc0) >> 3) : nullptr;
       if (n_iter > 0 && i_begin * BQ + r < p.T) {
         lse_nx = __ldg(p.lse + srow0 + i_begin * BQ + r);
         dl_nx = __ldg(p.delta + srow0 + i_begin * BQ + r);
+        if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + (srow0 + i_begin * BQ + r) * p.keep_pitch));
       }
       for (int n = 0; n < n_iter; ++n) {
         const int i = i_begin + n;
@@ -499,16 +514,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         const bool q_ok = q < p.T;
         const float lse = lse_nx - lg_scale;  // +inf -> P = 0 for rows past the sequence end
         const float dls = dl_nx * inv_s;
-        lse_nx = INFINITY; dl_nx = 0.f;
+        const uint32_t kbits = kb_nx;
+        lse_nx = INFINITY; dl_nx = 0.f; kb_nx = 0;
         if (n + 1 < n_iter && q + BQ < p.T) {
           lse_nx = __ldg(p.lse + srow0 + q + BQ);
           dl_nx = __ldg(p.delta + srow0 + q + BQ);
+          if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + (srow0 + q + BQ) * p.keep_pitch));
         }
-        const uint64_t row_id = static_cast<uint64_t>(srow0 + q);
         int lim = kv_len - k0;
         if (p.causal) lim = min(lim, q - k0 + 1);
         const bool full = __all_sync(0xffffffffu, lim >= BKV);
-        const uint64_t drop_base = row_id * groups_per_row + static_cast<uint64_t>((k0 + kc0) >> 3);
         mbar_wait(sdp_full, n & 1);
         tc_fence_after();
         // rolled loop over this thread's 4 groups of 8 keys, TMEM loads double buffered (compact loop body:
@@ -525,10 +540,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
               for (int t = 0; t < 8; ++t) pd[t] = t < rem ? pd[t] : 0.f;
             }
             if (use_drop) {
-              const uint4 bits = dst8.bits(drop_base + g);
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
-                const bool keep = dst8.keep(bits, t);
+                const bool keep = (kbits >> (8 * g + t)) & 1u;
                 const float u = keep ? __uint_as_float(rd[t]) : 0.f;
                 ds[t] = (pd[t] * p.scale) * (u - dls);
                 pd[t] = keep ? pd[t] : 0.f;
@@ -649,8 +663,8 @@ __global__ void dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat16* __
 
 using namespace mh;
 
-extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, int B, int T, int heads, int causal,
-                           float p_drop, uint64_t seed, uint32_t site, void* stream) {
+extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, uint8_t* keep_bits, int B, int T,
+                           int heads, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_fwd: bad shape B=%d T=%d heads=%d", B, T, heads);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int E = heads * HD;
@@ -669,6 +683,8 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
   p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop(p_drop, seed, site);
+  p.keep = keep_bits;
+  p.keep_pitch = ((T + 127) / 128) * 16;
   attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, tmkv, p);
   MH_LAUNCH_CHECK();
   ++g_launches;
@@ -676,9 +692,10 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
 }
 
 extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
-                           float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal, float p_drop,
-                           uint64_t seed, uint32_t site, void* stream) {
+                           const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
+                           int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_bwd: bad shape B=%d T=%d heads=%d", B, T, heads);
+  MH_CHECK(!(p_drop > 0.f) || keep_bits != nullptr, "attn_bwd: dropout needs the keep bits written by mh_attn_fwd");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int E = heads * HD;
   const long long rows = static_cast<long long>(B) * T;
@@ -709,6 +726,8 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
   p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop(p_drop, seed, site);
+  p.keep = keep_bits;
+  p.keep_pitch = ((T + 127) / 128) * 16;
   attn_bwd_kernel<<<dim3((T + BKV - 1) / BKV, heads, B), BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, tdq, p);
   MH_LAUNCH_CHECK();
   ++g_launches;

@@ -42,17 +42,17 @@ class _SelfAttentionFn(torch.autograd.Function):
         E = wo.shape[1]
         qkv = torch.empty(x.shape[0], 3 * E, device=x.device, dtype=torch.bfloat16)
         K.gemm(x, wqkv, qkv, bias=bqkv)
-        ctxv, lse = K.attn_fwd(qkv, kv_len, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site)
+        ctxv, lse, keep = K.attn_fwd(qkv, kv_len, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site)
         out = torch.empty(x.shape[0], wo.shape[0], device=x.device, dtype=torch.bfloat16)
         K.gemm(ctxv, wo, out, bias=bo)
         if any(ctx.needs_input_grad):
             ctx.mha, ctx.meta = mha, (B, T, heads, seed, site, causal, p_att)
-            ctx.save_for_backward(x, kv_len, qkv, ctxv, lse, wqkv, wo)
+            ctx.save_for_backward(x, kv_len, qkv, ctxv, lse, wqkv, wo, keep)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, kv_len, qkv, ctxv, lse, wqkv, wo = ctx.saved_tensors
+        x, kv_len, qkv, ctxv, lse, wqkv, wo, keep = ctx.saved_tensors
         mha = ctx.mha
         B, T, heads, seed, site, causal, p_att = ctx.meta
         E = wo.shape[1]
@@ -60,7 +60,7 @@ class _SelfAttentionFn(torch.autograd.Function):
         ops._wgrad(dout, ctxv, mha.out_proj)
         dctx = torch.empty_like(ctxv)
         K.gemm(dout, wo, dctx, b_mn=True)
-        dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site)
+        dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, keep, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site)
         for i, lin in enumerate((mha.q_proj, mha.k_proj, mha.v_proj)):
             ops._wgrad(dqkv, x, lin, col0=i * E, ncols=E)
         dx = None

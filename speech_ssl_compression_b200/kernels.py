@@ -84,27 +84,31 @@ def _call(name, *args):
 
 
 # ------------------------------------------------------------------------------ attention
-def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0):
-    """qkv: bf16 [B*T, 3*64*heads]; kv_len: int32 [B] (or None).  Returns (out [B*T, E], lse [B,H,T])."""
+def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0, want_keep=True):
+    """qkv: bf16 [B*T, 3*64*heads]; kv_len: int32 [B] (or None).
+    Returns (out [B*T, E], lse [B,H,T], keep bits u8 [B,H,T,16*ceil(T/128)] or None when p_drop == 0)."""
     E = 64 * heads
     if qkv.dtype != bf16 or tuple(qkv.shape) != (B * T, 3 * E) or not qkv.is_contiguous():
         raise ValueError(f"attn_fwd: qkv must be contiguous bf16 [{B * T}, {3 * E}], got {tuple(qkv.shape)}")
     out = torch.empty(B * T, E, device=qkv.device, dtype=bf16)
     lse = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
-    _call("mh_attn_fwd", _p(qkv), _p(kv_len), _p(out), _p(lse), c_int(B), c_int(T), c_int(heads), c_int(int(causal)),
-          _f(p_drop), c_uint64(seed), c_uint32(site), _s())
-    return out, lse
+    keep = None
+    if p_drop > 0.0 and want_keep:
+        keep = torch.empty(B, heads, T, 16 * ((T + 127) // 128), device=qkv.device, dtype=torch.uint8)
+    _call("mh_attn_fwd", _p(qkv), _p(kv_len), _p(out), _p(lse), _p(keep), c_int(B), c_int(T), c_int(heads),
+          c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), _s())
+    return out, lse, keep
 
 
-def attn_bwd(qkv, kv_len, out, dout, lse, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0):
+def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0):
     E = 64 * heads
     if dout.dtype != bf16 or not dout.is_contiguous() or tuple(dout.shape) != (B * T, E):
         raise ValueError("attn_bwd: dout must be contiguous bf16 [B*T, E]")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
     dq_acc = torch.empty(B * T, E, device=qkv.device, dtype=torch.float32)
-    _call("mh_attn_bwd", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(delta), _p(dq_acc), _p(dqkv), c_int(B),
-          c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), _s())
+    _call("mh_attn_bwd", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
+          c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), _s())
     return dqkv
 
 

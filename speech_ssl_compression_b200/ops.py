@@ -327,7 +327,7 @@ class EncoderLayerFn(torch.autograd.Function):
             a_in, mean0, rstd0 = K.layernorm_fwd(x, ln1.weight.detach(), ln1.bias.detach(), ln1.eps)
         qkv = torch.empty(M, 3 * E, device=dev, dtype=bf16)
         K.gemm(a_in, wqkv, qkv, bias=bqkv)
-        ctxv, lse = K.attn_fwd(qkv, kv_len, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site_base + SITE_ATTN)
+        ctxv, lse, keep = K.attn_fwd(qkv, kv_len, B, T, heads, causal=causal, p_drop=p_att, seed=seed, site=site_base + SITE_ATTN)
         y1 = torch.empty(M, C, device=dev, dtype=bf16)
         K.gemm(ctxv, wo, y1, epilogue=K.EPI_RES, bias=bo, aux_in=x, p_drop=p_res, seed=seed, site=site_base + SITE_DROP1)
         if pre_ln:
@@ -350,13 +350,13 @@ class EncoderLayerFn(torch.autograd.Function):
             ctx.layer = layer
             ctx.meta = (B, T, heads, seed, site_base, causal, p_res, p_act, p_att, pre_ln)
             ctx.save_for_backward(x, kv_len, a_in, qkv, ctxv, lse, y1, mean0, rstd0, mean1, rstd1, f_in, pre, u, y2, mean2,
-                                  rstd2, wqkv, wo, w1, w2)
+                                  rstd2, wqkv, wo, w1, w2, keep)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (x, kv_len, a_in, qkv, ctxv, lse, y1, mean0, rstd0, mean1, rstd1, f_in, pre, u, y2, mean2, rstd2, wqkv, wo, w1,
-         w2) = ctx.saved_tensors
+         w2, keep) = ctx.saved_tensors
         layer = ctx.layer
         mha = layer.self_attn
         B, T, heads, seed, site_base, causal, p_res, p_act, p_att, pre_ln = ctx.meta
@@ -397,7 +397,7 @@ class EncoderLayerFn(torch.autograd.Function):
         _wgrad(dz1, ctxv, mha.out_proj)
         dctx = torch.empty_like(ctxv)
         K.gemm(dz1, wo, dctx, b_mn=True)
-        dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, B, T, heads, causal=causal, p_drop=p_att, seed=seed,
+        dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, keep, B, T, heads, causal=causal, p_drop=p_att, seed=seed,
                           site=site_base + SITE_ATTN)
         _wgrad_qkv(dqkv, a_in, mha, E)
         dx = None

@@ -187,7 +187,8 @@ class TrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        ops.bump_weight_epoch()
+        ops.bump_weight_epoch()  # operand prep of masked / non-flat weights must be part of the captured step
+        self.flat._shadow_epoch = ops._EPOCH[0]  # (the bf16 shadow is current: written by the warm-up Adam steps)
         self.graph = torch.cuda.CUDAGraph()
         n0 = K.L.launch_count()
         rng_state = np.random.get_state()  # the per-layer layer-drop draws of the captured forward are replayed

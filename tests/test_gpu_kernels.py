@@ -177,13 +177,13 @@ def test_attention_fwd_bwd(B, T, H, lens, causal):
     E = 64 * H
     qkv = torch.randn(B * T, 3 * E, device=DEV).to(bf16)
     lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32)
-    out, lse = k.attn_fwd(qkv, lens_t, B, T, H, causal=causal)
+    out, lse, keep = k.attn_fwd(qkv, lens_t, B, T, H, causal=causal)
     qr = qkv.float().requires_grad_(True)
     ref = _ref_attn(qr, lens_t, B, T, H, causal)
     valid = (torch.arange(T, device=DEV)[None, :] < lens_t[:, None]).reshape(-1)
     assert rel(out[valid], ref[valid]) < 6e-3
     dout = torch.randn(B * T, E, device=DEV).to(bf16)
-    dqkv = k.attn_bwd(qkv, lens_t, out, dout, lse, B, T, H, causal=causal)
+    dqkv = k.attn_bwd(qkv, lens_t, out, dout, lse, keep, B, T, H, causal=causal)
     ref.backward(dout.float())
     g = qr.grad
     for sl in (slice(0, E), slice(E, 2 * E), slice(2 * E, 3 * E)):
@@ -200,8 +200,8 @@ def test_attention_dropout_is_regenerated_in_backward():
     B, T, H, p = 1, 128, 1, 0.25
     qkv = torch.randn(T, 192, device=DEV).to(bf16)
     lens_t = torch.tensor([T], device=DEV, dtype=torch.int32)
-    o1, lse = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=5, site=3)
-    o2, _ = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=5, site=3)
+    o1, lse, keep = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=5, site=3)
+    o2, _, _ = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=5, site=3)
     assert torch.equal(o1, o2)
     # recover the dropped probability matrix column block by column block with one-hot V
     P = torch.zeros(T, T, device=DEV)
@@ -209,12 +209,12 @@ def test_attention_dropout_is_regenerated_in_backward():
         q2 = qkv.clone()
         q2[:, 128:] = 0
         q2[c0:c0 + 64, 128:] = torch.eye(64, device=DEV).to(bf16)
-        oc, _ = k.attn_fwd(q2, lens_t, B, T, H, p_drop=p, seed=5, site=3)
+        oc, _, _ = k.attn_fwd(q2, lens_t, B, T, H, p_drop=p, seed=5, site=3)
         P[:, c0:c0 + 64] = oc.float()
     dropped = (P == 0).float().mean().item()
     assert abs(dropped - p) < 0.02
     dout = torch.randn(T, 64, device=DEV).to(bf16)
-    dqkv = k.attn_bwd(qkv, lens_t, o1, dout, lse, B, T, H, p_drop=p, seed=5, site=3)
+    dqkv = k.attn_bwd(qkv, lens_t, o1, dout, lse, keep, B, T, H, p_drop=p, seed=5, site=3)
     dv_ref = P.t() @ dout.float()
     assert rel(dqkv[:, 128:], dv_ref) < 1.5e-2
 

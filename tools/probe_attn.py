@@ -32,14 +32,14 @@ def run(B, T, H, lens, causal=False, bwd=True):
     E = 64 * H
     qkv = (torch.randn(B * T, 3 * E, device=dev) * 1.0).to(torch.bfloat16)
     lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
-    out, lse = K.attn_fwd(qkv, lens_t, B, T, H, causal=causal)
+    out, lse, keep = K.attn_fwd(qkv, lens_t, B, T, H, causal=causal)
     torch.cuda.synchronize()
     qr = qkv.float().requires_grad_(True)
     o_ref, _ = ref_attn(qr, lens_t, B, T, H, causal)
     print(f"fwd B={B} T={T} H={H} lens={lens} causal={causal}: rel={rel(out, o_ref):.3e}", flush=True)
     if bwd:
         dout = torch.randn(B * T, E, device=dev).to(torch.bfloat16)
-        dqkv = K.attn_bwd(qkv, lens_t, out, dout, lse, B, T, H, causal=causal)
+        dqkv = K.attn_bwd(qkv, lens_t, out, dout, lse, keep, B, T, H, causal=causal)
         torch.cuda.synchronize()
         o_ref.backward(dout.float())
         g = qr.grad
@@ -62,9 +62,9 @@ if which in ("all", "drop"):
     E = 64 * H
     qkv = torch.randn(B * T, 3 * E, device=dev).to(torch.bfloat16)
     lens_t = torch.tensor([256, 256], device=dev, dtype=torch.int32)
-    o0, _ = K.attn_fwd(qkv, lens_t, B, T, H)
-    o1, lse = K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=123, site=7)
-    o2, _ = K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=123, site=7)
+    o0, _, _ = K.attn_fwd(qkv, lens_t, B, T, H)
+    o1, lse, keep = K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=123, site=7)
+    o2, _, _ = K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=123, site=7)
     print("dropout deterministic:", torch.equal(o1, o2), " mean-ratio:", (o1.float().mean() / o0.float().mean()).item(),
           " rel(o1,o0):", rel(o1, o0))
 if which in ("all", "perf"):
@@ -73,10 +73,10 @@ if which in ("all", "perf"):
         qkv = torch.randn(B * T, 3 * E, device=dev).to(torch.bfloat16)
         lens_t = torch.full((B,), T, device=dev, dtype=torch.int32)
         dout = torch.randn(B * T, E, device=dev).to(torch.bfloat16)
-        out, lse = K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=1, site=1)
+        out, lse, keep = K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=1, site=1)
         for nm, fn, mult in (("fwd", lambda: K.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=1, site=1), 4),
                              ("fwd_nodrop", lambda: K.attn_fwd(qkv, lens_t, B, T, H), 4),
-                             ("bwd", lambda: K.attn_bwd(qkv, lens_t, out, dout, lse, B, T, H, p_drop=0.1, seed=1, site=1), 10)):
+                             ("bwd", lambda: K.attn_bwd(qkv, lens_t, out, dout, lse, keep, B, T, H, p_drop=0.1, seed=1, site=1), 10)):
             for _ in range(3): fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -12,7 +12,7 @@ qkv = torch.randn(B * T, 3 * E, device="cuda").to(torch.bfloat16)
 lens = torch.full((B,), T, device="cuda", dtype=torch.int32)
 dout = torch.randn(B * T, E, device="cuda").to(torch.bfloat16)
 for _ in range(3):
-    out, lse = K.attn_fwd(qkv, lens, B, T, H, p_drop=0.1, seed=1, site=1)
-    K.attn_bwd(qkv, lens, out, dout, lse, B, T, H, p_drop=0.1, seed=1, site=1)
+    out, lse, keep = K.attn_fwd(qkv, lens, B, T, H, p_drop=0.1, seed=1, site=1)
+    K.attn_bwd(qkv, lens, out, dout, lse, keep, B, T, H, p_drop=0.1, seed=1, site=1)
 torch.cuda.synchronize()
 print("ok")

@@ -46,6 +46,11 @@ struct AttnParams {
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
 __device__ __forceinline__ uint32_t swz(int r, int ch) { return r * 128 + ((ch ^ (r & 7)) << 4); }
 
+// 16-byte store to a 32-bit shared-window address (no 64-bit generic pointer arithmetic in the hot loops)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // rare path of the forward softmax (lazy rescaling): kept out of line so the hot loop stays small
 __device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
 #pragma unroll 1
@@ -363,53 +368,88 @@ struct AttnBwdParams {
   int keep_pitch;
 };
 
-// smem: K, V (16 KB each) | Q[2], dO[2] (64 KB) | P (32 KB) | dS (32 KB) | dQ staging 2 x [128 x 64] f32 (64 KB)
+// smem: K, V (16 KB each) | Q[3], dO[3] (96 KB) | P (32 KB) | dS (32 KB) | dQ staging [128 x 64] f32 (32 KB)
+//
+// Software pipeline of one CTA (per query block n; S / dP / dQ have ONE TMEM buffer each, the overlap comes from
+// splitting the element-wise work in two phases and interleaving the MMA issue order with them):
+//   compute warps :  A(n): S -> P (fp32 kept in registers, bf16 P_drop to smem)         -> arrive p_ready
+//                    drain dQ(n-1): TMEM -> fp32 staging -> TMA reduce-add
+//                    B(n): dP -> dS = P (c u - c delta) (bf16 to smem)                   -> arrive ds_ready
+//   MMA warp      :  [p_ready(n)]  dV += P^T dO(n);  S(n+1)            (runs under B(n) / drain)
+//                    [ds_ready(n)] dQ(n) = dS K;  dK += dS^T Q(n);  dP(n+1)   (runs under A(n+1) / drain dQ(n))
+// A commit on s_full(n+1) also covers dV(n) (P may be overwritten), one on dp_full(n+1) covers dQ(n) / dK(n)
+// (dS may be overwritten): no further barriers are needed for the single P / dS tiles.
 constexpr int BWD_DQ_STAGE = 128 * 64 * 4;
-constexpr int BWD_SMEM = TILE_BYTES * (2 + 4 + 2 + 2) + 2 * BWD_DQ_STAGE + 1024 + 256;
-constexpr int BWD_THREADS = 576;  // warps 0-15 compute, 16 = TMA, 17 = MMA
+constexpr int BWD_QST = 3;  // Q / dO ring depth: S(n+2) is issued in the middle of iteration n+1
+constexpr int BWD_KVLEN_CACHE = 256;
+constexpr int BWD_SMEM = TILE_BYTES * (2 + 2 * BWD_QST + 2 + 2) + BWD_DQ_STAGE + 1024 + 256 + BWD_KVLEN_CACHE * 4;
+constexpr int BWD_THREADS = 608;  // warps 0-15 compute, 16 = TMA loads, 17 = MMA, 18 = dQ reduce-add
 
+// Persistent: one CTA per SM walks the (batch, head, key block) work items with stride gridDim.x (key block
+// fastest, so the CTAs running at the same time share the Q / dO tiles of one head in L2).  Barriers, TMEM and
+// the Q / dO ring live across items: the producer runs ahead into the next item, whose K / V load only waits for
+// the last MMAs of the current one (a fresh CTA per item cost ~5 us of launch / allocation / first-load latency,
+// 25 % of the kernel at T = 750).
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tm_dkv,
+                const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE_BYTES;
-  uint8_t* sQ = sV + TILE_BYTES;        // 2 stages
-  uint8_t* sdO = sQ + 2 * TILE_BYTES;   // 2 stages
-  uint8_t* sP = sdO + 2 * TILE_BYTES;   // [128 q rows][128 keys] as 2 atoms of 64 keys
+  uint8_t* sQ = sV + TILE_BYTES;              // BWD_QST stages
+  uint8_t* sdO = sQ + BWD_QST * TILE_BYTES;   // BWD_QST stages
+  uint8_t* sP = sdO + BWD_QST * TILE_BYTES;   // [128 q rows][128 keys] as 2 atoms of 64 keys
   uint8_t* sdS = sP + 2 * TILE_BYTES;
-  uint8_t* sDQ = sdS + 2 * TILE_BYTES;  // 2 stages x 2 boxes of [128 rows x 32 f32], 128B-swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + 2 * BWD_DQ_STAGE);
+  uint8_t* sDQ = sdS + 2 * TILE_BYTES;        // 2 boxes of [128 rows x 32 f32], 128B-swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + BWD_DQ_STAGE);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;    // [2]
-  uint64_t* q_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;  // S and dP ready in TMEM
-  uint64_t* pds_full = bars + 6;  // P / dS written to smem (256 arrivals)
-  uint64_t* dq_full = bars + 7;   // dQ_i ready in TMEM (and all MMAs reading P / dS retired)
-  uint64_t* fin_full = bars + 8;  // dK / dV final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_empty = bars + 1;               // all MMAs of the item retired: K / V may be reloaded
+  uint64_t* q_full = bars + 2;                 // [BWD_QST]
+  uint64_t* q_empty = q_full + BWD_QST;        // [BWD_QST]
+  uint64_t* s_full = q_empty + BWD_QST;        // S_n ready in TMEM (and dV_{n-1} retired)
+  uint64_t* dp_full = s_full + 1;              // dP_n ready in TMEM (and dQ_{n-1}, dK_{n-1} retired)
+  uint64_t* p_ready = s_full + 2;              // P_n in smem, S_n consumed (16 arrivals: lane 0 of every compute warp)
+  uint64_t* ds_ready = s_full + 3;             // dS_n in smem, dP_n consumed, dQ_{n-1} drained (16 arrivals: lane 0 of every compute warp)
+  uint64_t* dq_full = s_full + 4;              // dQ_n ready in TMEM
+  uint64_t* fin_full = s_full + 5;             // dK / dV of the item final
+  uint64_t* acc_free = s_full + 6;             // dK / dV read out of TMEM (16 arrivals: lane 0 of every compute warp)
+  uint64_t* dq_staged = s_full + 7;            // dQ_n in the fp32 staging tile (16 arrivals)
+  uint64_t* dq_free = s_full + 8;              // the reduce-add of the staging tile has read it
+  uint64_t* kv_staged = s_full + 9;            // dK / dV of the item staged in the P / dS tiles (16 arrivals)
+  uint64_t* kv_st_free = s_full + 10;          // ... and read by their TMA stores
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 11);
+  int* s_kvlen = reinterpret_cast<int*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int k0 = kb * BKV;
-  const int kv_len = min(p.kv_len ? p.kv_len[b] : p.T, p.T);
-  const int n_q = (p.T + BQ - 1) / BQ;
-  const int i_begin = p.causal ? k0 / BQ : 0;  // query blocks that can see this key block
-  const bool active = k0 < kv_len;             // a fully padded key block has zero gradient
+  const int n_kb = (p.T + BKV - 1) / BKV;
+  const int n_items = n_kb * p.H * p.B;
+  const int n_q_all = (p.T + BQ - 1) / BQ;
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tmap_dq);
+    tma_prefetch_desc(&tm_dkv);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 512);
+    mbar_init(kv_empty, 1);
+    for (int s = 0; s < BWD_QST; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(p_ready, 16);
+    mbar_init(ds_ready, 16);
     mbar_init(dq_full, 1);
     mbar_init(fin_full, 1);
+    mbar_init(acc_free, 16);
+    mbar_init(dq_staged, 16);
+    mbar_init(dq_free, 1);
+    mbar_init(kv_staged, 16);
+    mbar_init(kv_st_free, 1);
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < BWD_KVLEN_CACHE && i < p.B; i += BWD_THREADS)
+    s_kvlen[i] = min(p.kv_len ? p.kv_len[i] : p.T, p.T);
   if (warp == 17) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -418,226 +458,341 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
                  tm_dq = tmem_base + 384;
 
-  if (active) {
-    if (warp == 16) {
-      if (elect_one()) {
-        mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-        tma_load_3d(sK, &tm_qkv, kv_full, p.E + h * HD, k0, b);
-        tma_load_3d(sV, &tm_qkv, kv_full, 2 * p.E + h * HD, k0, b);
-        for (int i = i_begin, n = 0; i < n_q; ++i, ++n) {
-          const int st = n & 1;
-          mbar_wait(&q_empty[st], ((n >> 1) & 1) ^ 1);
+  // work item -> (key block, head, batch); every role walks the same list and skips the same items
+  struct Item { int k0, h, b, kv_len, i_begin, n_iter; bool active; };
+  auto decode = [&](int item) {
+    Item w;
+    const int kb = item % n_kb;
+    const int bh = item / n_kb;
+    w.h = bh % p.H;
+    w.b = bh / p.H;
+    w.k0 = kb * BKV;
+    w.kv_len = w.b < BWD_KVLEN_CACHE ? s_kvlen[w.b] : min(p.kv_len ? p.kv_len[w.b] : p.T, p.T);
+    w.i_begin = p.causal ? w.k0 / BQ : 0;  // query blocks that can see this key block
+    w.n_iter = n_q_all - w.i_begin;
+    w.active = w.k0 < w.kv_len;            // a fully padded key block has zero gradient
+    return w;
+  };
+
+  if (warp == 16) {
+    if (elect_one()) {
+      int st = 0, ph = 0, cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item w = decode(item);
+        if (!w.active) continue;
+        // the first query blocks of the item go into the ring before K / V: their slots free up while the
+        // previous item is still finishing, K / V only after its last MMA
+        const int n_pre = min(w.n_iter, BWD_QST - 1);
+        auto load_q = [&](int n) {
+          mbar_wait(&q_empty[st], ph ^ 1);
           mbar_expect_tx(&q_full[st], 2 * TILE_BYTES);
-          tma_load_3d(sQ + st * TILE_BYTES, &tm_qkv, &q_full[st], h * HD, i * BQ, b);
-          tma_load_3d(sdO + st * TILE_BYTES, &tm_do, &q_full[st], h * HD, i * BQ, b);
-        }
-      }
-      __syncwarp();
-    } else if (warp == 17) {
-      if (elect_one()) {
-        const uint32_t id_s = make_idesc_bf16(BQ, BKV, false, false);   // S, dP: [q x k], both K-major
-        const uint32_t id_kv = make_idesc_bf16(BKV, HD, true, true);    // dV, dK: [k x hd], A and B MN-major
-        const uint32_t id_q = make_idesc_bf16(BQ, HD, false, true);     // dQ: [q x hd], A K-major, B MN-major
-        mbar_wait(kv_full, 0);
-        const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
-        auto issue_sdp = [&](int n) {
-          const int st = n & 1;
-          mbar_wait(&q_full[st], (n >> 1) & 1);
-          tc_fence_after();
-          const uint32_t aq = smem_u32(sQ + st * TILE_BYTES), ado = smem_u32(sdO + st * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tm_s, make_sdesc(aq + k * 32, 0, 1024), make_sdesc(ak + k * 32, 0, 1024), id_s, k > 0);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tm_dp, make_sdesc(ado + k * 32, 0, 1024), make_sdesc(av + k * 32, 0, 1024), id_s, k > 0);
-          umma_commit(sdp_full);
+          tma_load_3d(sQ + st * TILE_BYTES, &tm_qkv, &q_full[st], w.h * HD, (w.i_begin + n) * BQ, w.b);
+          tma_load_3d(sdO + st * TILE_BYTES, &tm_do, &q_full[st], w.h * HD, (w.i_begin + n) * BQ, w.b);
+          if (++st == BWD_QST) { st = 0; ph ^= 1; }
         };
-        const int n_iter = n_q - i_begin;
-        if (n_iter > 0) issue_sdp(0);
-        for (int n = 0; n < n_iter; ++n) {
-          const int st = n & 1;
-          mbar_wait(pds_full, n & 1);
+        for (int n = 0; n < n_pre; ++n) load_q(n);
+        if (cnt > 0) mbar_wait(kv_empty, (cnt - 1) & 1);
+        mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+        tma_load_3d(sK, &tm_qkv, kv_full, p.E + w.h * HD, w.k0, w.b);
+        tma_load_3d(sV, &tm_qkv, kv_full, 2 * p.E + w.h * HD, w.k0, w.b);
+        for (int n = n_pre; n < w.n_iter; ++n) load_q(n);
+        ++cnt;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    if (elect_one()) {
+      const uint32_t id_s = make_idesc_bf16(BQ, BKV, false, false);   // S, dP: [q x k], both K-major
+      const uint32_t id_kv = make_idesc_bf16(BKV, HD, true, true);    // dV, dK: [k x hd], A and B MN-major
+      const uint32_t id_q = make_idesc_bf16(BQ, HD, false, true);     // dQ: [q x hd], A K-major, B MN-major
+      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
+      int st = 0, ph = 0;  // ring slot / phase of the current query block
+      int cnt = 0;         // active items done
+      uint32_t it = 0;     // query-block iterations done (parity of the per-iteration barriers)
+      
+      auto issue_s = [&](int slot) {
+        const uint32_t aq = smem_u32(sQ + slot * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tm_s, make_sdesc(aq + k * 32, 0, 1024), make_sdesc(ak + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(s_full);
+      };
+      auto issue_dp = [&](int slot) {
+        const uint32_t ado = smem_u32(sdO + slot * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tm_dp, make_sdesc(ado + k * 32, 0, 1024), make_sdesc(av + k * 32, 0, 1024), id_s, k > 0);
+        umma_commit(dp_full);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item w = decode(item);
+        if (!w.active) continue;
+        mbar_wait(kv_full, cnt & 1);
+        if (w.n_iter > 0) {
+          mbar_wait(&q_full[st], ph);
           tc_fence_after();
+          issue_s(st);
+          issue_dp(st);
+        }
+        for (int n = 0; n < w.n_iter; ++n, ++it) {
+          int st1 = st + 1, ph1 = ph;
+          if (st1 == BWD_QST) { st1 = 0; ph1 ^= 1; }
           const uint32_t aq = smem_u32(sQ + st * TILE_BYTES), ado = smem_u32(sdO + st * TILE_BYTES);
-          // dQ_i = dS K (contraction over the 128 keys) first: the compute warps turn it into the global
-          // reduce-add while dV / dK and the next S / dP are still on the tensor pipe
+          // ---- P_n is in smem: dV += P^T dO (contraction over the 128 query rows), then S_{n+1}
+          mbar_wait(p_ready, it & 1);
+          if (n == 0 && cnt > 0) mbar_wait(acc_free, (cnt - 1) & 1);  // previous item's dK / dV read out
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BQ / 16; ++k) {
+            umma_bf16(tm_dv, make_sdesc(ap + k * 2048, TILE_BYTES, 1024), make_sdesc(ado + k * 2048, TILE_BYTES, 1024),
+                      id_kv, (n > 0 || k > 0) ? 1u : 0u);
+          }
+          if (n + 1 < w.n_iter) {
+            mbar_wait(&q_full[st1], ph1);
+            tc_fence_after();
+            issue_s(st1);
+          }
+          // ---- dS_n is in smem: dQ_n = dS K (contraction over the 128 keys), dK += dS^T Q, then dP_{n+1}
+          mbar_wait(ds_ready, it & 1);
+          tc_fence_after();
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             umma_bf16(tm_dq, make_sdesc(ads + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
                       make_sdesc(ak + k * 2048, TILE_BYTES, 1024), id_q, k > 0);
           }
           umma_commit(dq_full);
-          // contraction over the 128 query rows: 8 steps of 16 rows (2048 B per step in every tile)
-#pragma unroll
-          for (int k = 0; k < BQ / 16; ++k) {
-            umma_bf16(tm_dv, make_sdesc(ap + k * 2048, TILE_BYTES, 1024), make_sdesc(ado + k * 2048, TILE_BYTES, 1024),
-                      id_kv, (n > 0 || k > 0) ? 1u : 0u);
-          }
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k) {
             umma_bf16(tm_dk, make_sdesc(ads + k * 2048, TILE_BYTES, 1024), make_sdesc(aq + k * 2048, TILE_BYTES, 1024),
                       id_kv, (n > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&q_empty[st]);
-          if (n + 1 < n_iter) issue_sdp(n + 1);
+          if (n + 1 < w.n_iter) issue_dp(st1);
+          st = st1; ph = ph1;
         }
         umma_commit(fin_full);
+        umma_commit(kv_empty);
+        ++cnt;
       }
-      __syncwarp();
-    } else {
-      // ---------------------------------------------------------------- compute warps
-      // thread = (row r of the tile, 32-column part): S / dP / dQ rows are queries, dK / dV rows are keys
-      const int quad = warp & 3, part = warp >> 2;
-      const int r = quad * 32 + lane;
-      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const int n_iter = n_q - i_begin;
-      const int kc0 = part * 32;
-      const bool use_drop = p.drop.thresh != 0;
-      // keep-scale s = 1/(1-p) folded into the exponent: pr' = s * P.  With u = keep ? dP : 0:
-      //   P_drop = keep ? pr' : 0,   dS = P (s u - delta) c = pr' c (u - delta / s)
-      const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
-      const float inv_s = use_drop ? 1.f / p.drop.scale : 1.f;
-      const long long srow0 = (static_cast<long long>(b) * p.H + h) * p.T;
-      // per-row statistics of the next query block are fetched one iteration ahead
-      float lse_nx = INFINITY, dl_nx = 0.f;
-      uint32_t kb_nx = 0;  // keep bits of this thread's 32 keys for the next query row
-      const uint8_t* keep_col = use_drop ? p.keep + ((k0 + kc0) >> 3) : nullptr;
-      if (n_iter > 0 && i_begin * BQ + r < p.T) {
-        lse_nx = __ldg(p.lse + srow0 + i_begin * BQ + r);
-        dl_nx = __ldg(p.delta + srow0 + i_begin * BQ + r);
-        if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + (srow0 + i_begin * BQ + r) * p.keep_pitch));
-      }
-      for (int n = 0; n < n_iter; ++n) {
-        const int i = i_begin + n;
-        const int q = i * BQ + r;
-        const bool q_ok = q < p.T;
-        const float lse = lse_nx - lg_scale;  // +inf -> P = 0 for rows past the sequence end
-        const float dls = dl_nx * inv_s;
-        const uint32_t kbits = kb_nx;
-        lse_nx = INFINITY; dl_nx = 0.f; kb_nx = 0;
-        if (n + 1 < n_iter && q + BQ < p.T) {
-          lse_nx = __ldg(p.lse + srow0 + q + BQ);
-          dl_nx = __ldg(p.delta + srow0 + q + BQ);
-          if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + (srow0 + q + BQ) * p.keep_pitch));
+    }
+    __syncwarp();
+  } else if (warp == 18) {
+    // dQ_n: fp32 staging tile -> TMA reduce-add into the dQ workspace, one per 32-column box (full 128-byte lines
+    // instead of per-thread 16-byte REDs).  A warp of its own: issuing the two bulk reductions and waiting for
+    // their smem reads cost the compute warp that used to do it ~1100 clk per query block.
+    if (elect_one()) {
+      uint32_t dcount = 0;
+      int cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item w = decode(item);
+        if (!w.active) continue;
+        for (int n = 0; n < w.n_iter; ++n, ++dcount) {
+          mbar_wait(dq_staged, dcount & 1);
+          tma_reduce_add_3d(&tmap_dq, sDQ, w.h * HD, (w.i_begin + n) * BQ, w.b);
+          tma_reduce_add_3d(&tmap_dq, sDQ + 128 * 128, w.h * HD + 32, (w.i_begin + n) * BQ, w.b);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(dq_free);
         }
-        int lim = kv_len - k0;
-        if (p.causal) lim = min(lim, q - k0 + 1);
-        const bool full = __all_sync(0xffffffffu, lim >= BKV);
-        mbar_wait(sdp_full, n & 1);
+        // dK / dV of the item: bf16 tiles staged in the (now idle) P / dS buffers -> two TMA tile stores (rows past
+        // the sequence end are clipped by the tensor map)
+        mbar_wait(kv_staged, cnt & 1);
+        tma_store_3d(&tm_dkv, sP, p.E + w.h * HD, w.k0, w.b);
+        tma_store_3d(&tm_dkv, sdS, 2 * p.E + w.h * HD, w.k0, w.b);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(kv_st_free);
+        ++cnt;
+      }
+      bulk_wait0();
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    // thread = (row r of the tile, 32-column part): S / dP / dQ rows are queries, dK / dV rows are keys
+    const int quad = warp & 3, part = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int kc0 = part * 32;
+    const bool use_drop = p.drop.thresh != 0;
+    // keep-scale s = 1/(1-p) folded into the exponent: pr' = s * P.  With u = keep ? dP : 0:
+    //   P_drop = keep ? pr' : 0,   dS = P (s u - delta) c = pr' (c u - c delta / s)
+    const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
+    const float inv_s = (use_drop ? 1.f / p.drop.scale : 1.f) * p.scale;
+    // this thread's 64 bytes of its P row (dS: + 2 tiles): atom (kc0 >> 6), row r, 16-byte chunks ch0 .. ch0 + 3
+    const uint32_t p_row = smem_u32(sP) + (kc0 >> 6) * TILE_BYTES + r * 128;
+    const int ch0 = (kc0 & 63) >> 3;
+    const uint32_t dq_box = smem_u32(sDQ) + (part >> 1) * (128 * 128) + r * 128;
+    int cnt = 0;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item w = decode(item);
+      const int key = w.k0 + r;
+      __nv_bfloat16* const kv_out =
+          p.dqkv + (static_cast<long long>(w.b) * p.T + key) * (3LL * p.E) + w.h * HD + part * 16;
+      if (!w.active) {
+        // fully padded key block: dK = dV = 0
+        if (key < p.T) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            stg128(kv_out + p.E + g * 8, make_uint4(0, 0, 0, 0));
+            stg128(kv_out + 2 * p.E + g * 8, make_uint4(0, 0, 0, 0));
+          }
+        }
+        continue;
+      }
+      // per-row statistics (lse, delta, 32 keep bits) of the next query block are fetched one iteration ahead;
+      // addressing is a single 32-bit row index (B H T < 2^31 rows) so the loop carries one register for it
+      int srow = (w.b * p.H + w.h) * p.T + w.i_begin * BQ + r;  // (b, h, query) row of this thread in lse / delta / keep
+      int q_nx = w.i_begin * BQ + r;
+      const uint8_t* const keep_col = use_drop ? p.keep + ((w.k0 + kc0) >> 3) : nullptr;
+      float lse_nx = INFINITY, dl_nx = 0.f;
+      uint32_t kb_nx = 0xffffffffu;  // keep bits of this thread's 32 keys for the next query row
+      if (w.n_iter > 0 && q_nx < p.T) {
+        lse_nx = __ldg(p.lse + srow);
+        dl_nx = __ldg(p.delta + srow);
+        if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+      }
+      // dQ of iteration `g` (global count): this warp's 16 of the 64 head-dim columns -> fp32 staging tile, which
+      // warp 18 adds into the dQ workspace
+      auto drain_dq = [&](uint32_t g) {
+        mbar_wait(dq_full, g & 1);
+        mbar_wait(dq_free, (g & 1) ^ 1);  // reduce-add g - 1 has read the staging tile (passes at once for g = 0)
         tc_fence_after();
-        // rolled loop over this thread's 4 groups of 8 keys, TMEM loads double buffered (compact loop body:
-        // instruction fetch, not issue slots, limited the fully unrolled form)
-        {
-          uint32_t sa[8], da[8], sb[8], db[8];
-          auto emit = [&](const uint32_t (&rs)[8], const uint32_t (&rd)[8], int g) {
-            float pd[8], ds[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) pd[t] = ex2_approx(fmaf(__uint_as_float(rs[t]), p.scale_log2, -lse));
-            const int rem = lim - (kc0 + g * 8);
-            if (rem < 8) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) pd[t] = t < rem ? pd[t] : 0.f;
-            }
-            if (use_drop) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const bool keep = (kbits >> (8 * g + t)) & 1u;
-                const float u = keep ? __uint_as_float(rd[t]) : 0.f;
-                ds[t] = (pd[t] * p.scale) * (u - dls);
-                pd[t] = keep ? pd[t] : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) ds[t] = (pd[t] * p.scale) * (__uint_as_float(rd[t]) - dls);
-            }
-            const int kc = kc0 + g * 8;
-            const uint32_t off = (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
-            *reinterpret_cast<uint4*>(sP + off) = f32_to_bf16x8(pd);
-            *reinterpret_cast<uint4*>(sdS + off) = f32_to_bf16x8(ds);
-          };
-          tmem_ld8(tm_s + lane_off + kc0, sa);
-          tmem_ld8(tm_dp + lane_off + kc0, da);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t rq[8];
+          tmem_ld8(tm_dq + lane_off + part * 16 + hf * 8, rq);
           tmem_ld_wait();
-#pragma unroll 1
-          for (int g = 0; g < 4; g += 2) {
-            tmem_ld8(tm_s + lane_off + kc0 + (g + 1) * 8, sb);
-            tmem_ld8(tm_dp + lane_off + kc0 + (g + 1) * 8, db);
-            emit(sa, da, g);
-            tmem_ld_wait();
-            if (g + 2 < 4) {
-              tmem_ld8(tm_s + lane_off + kc0 + (g + 2) * 8, sa);
-              tmem_ld8(tm_dp + lane_off + kc0 + (g + 2) * 8, da);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            sts128(dq_box + ((((part & 1) * 4 + hf * 2 + t) ^ (r & 7)) << 4),
+                   make_uint4(rq[4 * t], rq[4 * t + 1], rq[4 * t + 2], rq[4 * t + 3]));
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_staged);
+      };
+      for (int n = 0; n < w.n_iter; ++n, ++it) {
+        const int q = q_nx;
+        const float lse = lse_nx - lg_scale;  // +inf -> P = 0 for rows past the sequence end
+        const float dls = dl_nx * inv_s;      // c * delta / s
+        const uint32_t kbits = kb_nx;
+        lse_nx = INFINITY; dl_nx = 0.f; kb_nx = 0xffffffffu;
+        q_nx += BQ; srow += BQ;
+        if (n + 1 < w.n_iter && q_nx < p.T) {
+          lse_nx = __ldg(p.lse + srow);
+          dl_nx = __ldg(p.delta + srow);
+          if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+        }
+        int lim = w.kv_len - w.k0;
+        if (p.causal) lim = min(lim, q - w.k0 + 1);
+        const int rem0 = lim - kc0;  // visible keys among this thread's 32
+        // unmasked probabilities (x keep-scale) of this thread's 32 keys, kept as bf16 pairs between the two phases:
+        // fp32 copies cost 16 more registers than the 96 a 19-warp CTA leaves per thread (spills in the hot loop)
+        uint32_t pk[16];
+        // ---- phase A: P = exp2(S c - lse), P_drop (bf16) -> smem
+        if (n == 0 && cnt > 0) mbar_wait(kv_st_free, (cnt - 1) & 1);  // previous item's dK / dV left the P / dS tiles
+        mbar_wait(s_full, it & 1);
+        tc_fence_after();
+        {
+          uint32_t sa[16], sb[16];
+          tmem_ld16(tm_s + lane_off + kc0, sa);
+          tmem_ld_wait();
+          tmem_ld16(tm_s + lane_off + kc0 + 16, sb);  // in flight under the first half's exponentials
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1) tmem_ld_wait();
+            float pr[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+              pr[t] = ex2_approx(fmaf(__uint_as_float(half == 0 ? sa[t] : sb[t]), p.scale_log2, -lse));
+            if (rem0 < 32) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) pr[t] = 16 * half + t < rem0 ? pr[t] : 0.f;
             }
-            emit(sb, db, g + 1);
-            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 8; ++t) pk[8 * half + t] = pack_bf16(pr[2 * t], pr[2 * t + 1]);
+#pragma unroll
+            for (int g = 2 * half; g < 2 * half + 2; ++g) {
+              // dropped keys: zero the 16-bit halves of the packed pairs
+              uint32_t w4[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const uint32_t two = kbits >> (8 * g + 2 * t);
+                const uint32_t m = ((two & 1u) ? 0x0000ffffu : 0u) | ((two & 2u) ? 0xffff0000u : 0u);
+                w4[t] = pk[4 * g + t] & m;
+              }
+              sts128(p_row + (((ch0 + g) ^ (r & 7)) << 4), make_uint4(w4[0], w4[1], w4[2], w4[3]));
+            }
           }
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(pds_full);
-        // dQ_i: this warp's 16 of the 64 head-dim columns -> fp32 staging tile -> one TMA reduce-add per
-        // 32-column box (full 128-byte lines into the fp32 dQ workspace instead of per-thread 16-byte REDs)
-        mbar_wait(dq_full, n & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);  // one arrival per warp: 512 arrivals on one mbarrier serialise
+        // ---- dQ of the previous query block (its MMA ran under phase A)
+        if (n > 0) drain_dq(it - 1);
+        // ---- phase B: dS = P (c u - c delta / s), bf16 -> smem
+        mbar_wait(dp_full, it & 1);
         tc_fence_after();
         {
-          uint32_t rq[16];
-          tmem_ld16(tm_dq + lane_off + part * 16, rq);
+          uint32_t da[8], db[8];
+          tmem_ld8(tm_dp + lane_off + kc0, da);
           tmem_ld_wait();
-          uint8_t* box = sDQ + (n & 1) * BWD_DQ_STAGE + (part >> 1) * (128 * 128);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            *reinterpret_cast<uint4*>(box + r * 128 + ((((part & 1) * 4 + t) ^ (r & 7)) << 4)) =
-                make_uint4(rq[4 * t], rq[4 * t + 1], rq[4 * t + 2], rq[4 * t + 3]);
+          for (int g = 0; g < 4; ++g) {
+            // the next group's dP is in flight while this one is turned into dS
+            if (g + 1 < 4) tmem_ld8(tm_dp + lane_off + kc0 + (g + 1) * 8, (g & 1) ? da : db);
+            float ds[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const uint32_t raw = (g & 1) ? db[t] : da[t];
+              const float u = ((kbits >> (8 * g + t)) & 1u) ? __uint_as_float(raw) : 0.f;
+              const uint32_t pw = pk[4 * g + (t >> 1)];
+              ds[t] = ((t & 1) ? bf16_hi(pw) : bf16_lo(pw)) * fmaf(u, p.scale, -dls);
+            }
+            sts128(p_row + 2 * TILE_BYTES + (((ch0 + g) ^ (r & 7)) << 4), f32_to_bf16x8(ds));
+            if (g + 1 < 4) tmem_ld_wait();
+          }
         }
-        tc_fence_before();
         fence_proxy_async_smem();
-        // the group issued one iteration ago has long finished reading the other stage: waiting for it here,
-        // before the barrier, tells every thread that the stage written next iteration is free
-        if (threadIdx.x == 0) bulk_wait_read0();
-        bar_sync(1, 512);
-        if (threadIdx.x == 0) {
-          const uint8_t* src = sDQ + (n & 1) * BWD_DQ_STAGE;
-          tma_reduce_add_3d(&tmap_dq, src, h * HD, i * BQ, b);
-          tma_reduce_add_3d(&tmap_dq, src + 128 * 128, h * HD + 32, i * BQ, b);
-          bulk_commit();
-        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_ready);
       }
-      if (threadIdx.x == 0) bulk_wait0();
+      if (w.n_iter > 0) drain_dq(it - 1);
       // final dK / dV: row r = key k0 + r, this warp's 16 head-dim columns
-      mbar_wait(fin_full, 0);
+      mbar_wait(fin_full, cnt & 1);
       tc_fence_after();
-      const int key = k0 + r;
-      uint32_t rk[16], rv[16];
-      tmem_ld16(tm_dk + lane_off + part * 16, rk);
-      tmem_ld16(tm_dv + lane_off + part * 16, rv);
-      tmem_ld_wait();
-      if (key < p.T) {
-        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + part * 16;
+      {
+        // row r = key k0 + r, this warp's 16 head-dim columns = 16-byte chunks 2 part, 2 part + 1 of the 128-byte row
+        uint32_t rk[16], rv[16];
+        tmem_ld16(tm_dk + lane_off + part * 16, rk);
+        tmem_ld16(tm_dv + lane_off + part * 16, rv);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        const uint32_t row = smem_u32(sP) + r * 128;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           float a[8], c[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            a[t] = n_iter > 0 ? __uint_as_float(rk[g * 8 + t]) : 0.f;
-            c[t] = n_iter > 0 ? __uint_as_float(rv[g * 8 + t]) : 0.f;
+            a[t] = w.n_iter > 0 ? __uint_as_float(rk[g * 8 + t]) : 0.f;
+            c[t] = w.n_iter > 0 ? __uint_as_float(rv[g * 8 + t]) : 0.f;
           }
-          stg128(base + p.E + g * 8, f32_to_bf16x8(a));
-          stg128(base + 2 * p.E + g * 8, f32_to_bf16x8(c));
+          const uint32_t off = ((2 * part + g) ^ (r & 7)) << 4;
+          sts128(row + off, f32_to_bf16x8(a));
+          sts128(row + 2 * TILE_BYTES + off, f32_to_bf16x8(c));
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kv_staged);
       }
-    }
-  } else if (warp < 16) {
-    // fully padded key block: dK = dV = 0
-    const int r = (warp & 3) * 32 + lane, part = warp >> 2;
-    const int key = k0 + r;
-    if (key < p.T) {
-      __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3LL * p.E) + h * HD + part * 16;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        stg128(base + p.E + g * 8, make_uint4(0, 0, 0, 0));
-        stg128(base + 2 * p.E + g * 8, make_uint4(0, 0, 0, 0));
-      }
+      ++cnt;
     }
   }
   tc_fence_before();
@@ -704,6 +859,9 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   if (rc) return rc;
   rc = make_tmap_3d(&tdo, dout, E, T, B, E, static_cast<long long>(T) * E, HD, BQ);
   if (rc) return rc;
+  CUtensorMap tdkv;
+  rc = make_tmap_3d(&tdkv, dqkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, BKV);
+  if (rc) return rc;
   CUtensorMap tdq;
   rc = make_tmap_3d(&tdq, dq_acc, E, T, B, E, static_cast<long long>(T) * E, 32, BQ, 4);
   if (rc) return rc;
@@ -728,7 +886,12 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   p.drop = make_drop(p_drop, seed, site);
   p.keep = keep_bits;
   p.keep_pitch = ((T + 127) / 128) * 16;
-  attn_bwd_kernel<<<dim3((T + BKV - 1) / BKV, heads, B), BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, tdq, p);
+  {
+    const long long items = static_cast<long long>((T + BKV - 1) / BKV) * heads * B;
+    MH_CHECK(items < (1LL << 31), "attn_bwd: too many work items");
+    const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
+    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, tdq, tdkv, p);
+  }
   MH_LAUNCH_CHECK();
   ++g_launches;
   long long g = (rows * (E / 8) + 255) / 256;

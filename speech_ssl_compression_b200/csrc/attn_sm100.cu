@@ -404,8 +404,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sdS = sP + 2 * TILE_BYTES;
   uint8_t* sDQ = sdS + 2 * TILE_BYTES;        // 2 boxes of [128 rows x 32 f32], 128B-swizzled
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + BWD_DQ_STAGE);
-  uint64_t* kv_full = bars;
-  uint64_t* kv_empty = bars + 1;               // all MMAs of the item retired: K / V may be reloaded
+  uint64_t* k_full = bars;                     // K / V of the item loaded
+  uint64_t* v_full = bars + 1;
+  uint64_t* k_empty = bars + 20;               // last MMA reading K (dQ of the last query block) retired
+  uint64_t* v_empty = bars + 21;               // last MMA reading V (dP of the last query block) retired
   uint64_t* q_full = bars + 2;                 // [BWD_QST]
   uint64_t* q_empty = q_full + BWD_QST;        // [BWD_QST]
   uint64_t* s_full = q_empty + BWD_QST;        // S_n ready in TMEM (and dV_{n-1} retired)
@@ -432,8 +434,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tmap_dq);
     tma_prefetch_desc(&tm_dkv);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_empty, 1);
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_empty, 1);
     for (int s = 0; s < BWD_QST; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
@@ -480,8 +484,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const Item w = decode(item);
         if (!w.active) continue;
-        // the first query blocks of the item go into the ring before K / V: their slots free up while the
-        // previous item is still finishing, K / V only after its last MMA
+        // Loads are issued in the order their buffers free up while the previous item finishes: V (last read by the
+        // dP of its last query block), the first two query blocks, K (last read by the last dQ), the rest.
         const int n_pre = min(w.n_iter, BWD_QST - 1);
         auto load_q = [&](int n) {
           mbar_wait(&q_empty[st], ph ^ 1);
@@ -490,11 +494,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           tma_load_3d(sdO + st * TILE_BYTES, &tm_do, &q_full[st], w.h * HD, (w.i_begin + n) * BQ, w.b);
           if (++st == BWD_QST) { st = 0; ph ^= 1; }
         };
+        if (cnt > 0) mbar_wait(v_empty, (cnt - 1) & 1);
+        mbar_expect_tx(v_full, TILE_BYTES);
+        tma_load_3d(sV, &tm_qkv, v_full, 2 * p.E + w.h * HD, w.k0, w.b);
         for (int n = 0; n < n_pre; ++n) load_q(n);
-        if (cnt > 0) mbar_wait(kv_empty, (cnt - 1) & 1);
-        mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-        tma_load_3d(sK, &tm_qkv, kv_full, p.E + w.h * HD, w.k0, w.b);
-        tma_load_3d(sV, &tm_qkv, kv_full, 2 * p.E + w.h * HD, w.k0, w.b);
+        if (cnt > 0) mbar_wait(k_empty, (cnt - 1) & 1);
+        mbar_expect_tx(k_full, TILE_BYTES);
+        tma_load_3d(sK, &tm_qkv, k_full, p.E + w.h * HD, w.k0, w.b);
         for (int n = n_pre; n < w.n_iter; ++n) load_q(n);
         ++cnt;
       }
@@ -527,12 +533,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const Item w = decode(item);
         if (!w.active) continue;
-        mbar_wait(kv_full, cnt & 1);
         if (w.n_iter > 0) {
+          mbar_wait(k_full, cnt & 1);
           mbar_wait(&q_full[st], ph);
           tc_fence_after();
           issue_s(st);
+          mbar_wait(v_full, cnt & 1);
+          tc_fence_after();
           issue_dp(st);
+          if (w.n_iter == 1) umma_commit(v_empty);
         }
         for (int n = 0; n < w.n_iter; ++n, ++it) {
           int st1 = st + 1, ph1 = ph;
@@ -561,17 +570,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                       make_sdesc(ak + k * 2048, TILE_BYTES, 1024), id_q, k > 0);
           }
           umma_commit(dq_full);
+          if (n + 1 == w.n_iter) umma_commit(k_empty);
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k) {
             umma_bf16(tm_dk, make_sdesc(ads + k * 2048, TILE_BYTES, 1024), make_sdesc(aq + k * 2048, TILE_BYTES, 1024),
                       id_kv, (n > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&q_empty[st]);
-          if (n + 1 < w.n_iter) issue_dp(st1);
+          if (n + 1 < w.n_iter) {
+            issue_dp(st1);
+            if (n + 2 == w.n_iter) umma_commit(v_empty);
+          }
           st = st1; ph = ph1;
         }
         umma_commit(fin_full);
-        umma_commit(kv_empty);
         ++cnt;
       }
     }
@@ -625,6 +637,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t dq_box = smem_u32(sDQ) + (part >> 1) * (128 * 128) + r * 128;
     int cnt = 0;
     uint32_t it = 0;
+    float lse_nx = INFINITY, dl_nx = 0.f;
+    uint32_t kb_nx = 0xffffffffu;  // keep bits of this thread's 32 keys for the next query row
+    bool pref = false;             // lse_nx / dl_nx / kb_nx already hold the first query block of the coming item
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item w = decode(item);
       const int key = w.k0 + r;
@@ -646,13 +661,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       int srow = (w.b * p.H + w.h) * p.T + w.i_begin * BQ + r;  // (b, h, query) row of this thread in lse / delta / keep
       int q_nx = w.i_begin * BQ + r;
       const uint8_t* const keep_col = use_drop ? p.keep + ((w.k0 + kc0) >> 3) : nullptr;
-      float lse_nx = INFINITY, dl_nx = 0.f;
-      uint32_t kb_nx = 0xffffffffu;  // keep bits of this thread's 32 keys for the next query row
-      if (w.n_iter > 0 && q_nx < p.T) {
-        lse_nx = __ldg(p.lse + srow);
-        dl_nx = __ldg(p.delta + srow);
-        if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+      if (!pref) {  // (normally fetched during the last query block of the previous item)
+        lse_nx = INFINITY; dl_nx = 0.f; kb_nx = 0xffffffffu;
+        if (w.n_iter > 0 && q_nx < p.T) {
+          lse_nx = __ldg(p.lse + srow);
+          dl_nx = __ldg(p.delta + srow);
+          if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+        }
       }
+      pref = false;
       // dQ of iteration `g` (global count): this warp's 16 of the 64 head-dim columns -> fp32 staging tile, which
       // warp 18 adds into the dQ workspace
       auto drain_dq = [&](uint32_t g) {
@@ -681,10 +698,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         const uint32_t kbits = kb_nx;
         lse_nx = INFINITY; dl_nx = 0.f; kb_nx = 0xffffffffu;
         q_nx += BQ; srow += BQ;
-        if (n + 1 < w.n_iter && q_nx < p.T) {
-          lse_nx = __ldg(p.lse + srow);
-          dl_nx = __ldg(p.delta + srow);
-          if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+        if (n + 1 < w.n_iter) {
+          if (q_nx < p.T) {
+            lse_nx = __ldg(p.lse + srow);
+            dl_nx = __ldg(p.delta + srow);
+            if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+          }
+        } else if (item + static_cast<int>(gridDim.x) < n_items) {
+          // last query block: fetch the first block's statistics of the next item (hides the load latency and the
+          // item decode behind this block's work instead of exposing them at the item boundary)
+          const Item wn = decode(item + gridDim.x);
+          if (wn.active) {
+            pref = true;
+            const int q0 = wn.i_begin * BQ + r;
+            if (wn.n_iter > 0 && q0 < p.T) {
+              const int row = (wn.b * p.H + wn.h) * p.T + q0;
+              lse_nx = __ldg(p.lse + row);
+              dl_nx = __ldg(p.delta + row);
+              if (use_drop)
+                kb_nx = __ldg(reinterpret_cast<const uint32_t*>(p.keep + ((wn.k0 + kc0) >> 3) + static_cast<long long>(row) * p.keep_pitch));
+            }
+          }
         }
         int lim = w.kv_len - w.k0;
         if (p.causal) lim = min(lim, q - w.k0 + 1);

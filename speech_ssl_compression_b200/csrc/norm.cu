@@ -101,18 +101,40 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
 
+  // The row is kept as the raw bf16 it was loaded as (and unpacked twice) instead of as fp32 products: that leaves
+  // the registers to have the NEXT row's loads in flight while this one is reduced and written -- the kernel is
+  // HBM-bound and a load -> shuffle-reduce -> store sequence per row left the memory pipe idle half of the time.
+  uint4 nd[NCH], nx[NCH];
+  float nmean = 0.f, nrstd = 0.f;
+  auto fetch = [&](int row) {
+    const long long off = static_cast<long long>(row) * cols;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        nd[i] = ldg128(dy + off + c * 8);
+        nx[i] = ldg128(x + off + c * 8);
+      }
+    }
+    nmean = __ldg(mean_in + row);
+    nrstd = __ldg(rstd_in + row);
+  };
+  if (warp_global < rows) fetch(warp_global);
   for (int row = warp_global; row < rows; row += nwarps) {
     const long long off = static_cast<long long>(row) * cols;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float gy[NCH][8], xh[NCH][8];
+    uint4 rd[NCH], rx[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { rd[i] = nd[i]; rx[i] = nx[i]; }
+    const float mean = nmean, rstd = nrstd;
+    if (row + nwarps < rows) fetch(row + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
         float d[8], xv[8];
-        bf16x8_to_f32(ldg128(dy + off + c * 8), d);
-        bf16x8_to_f32(ldg128(x + off + c * 8), xv);
+        bf16x8_to_f32(rd[i], d);
+        bf16x8_to_f32(rx[i], xv);
         if (din.thresh != 0) {
           drop_apply8(din, static_cast<uint64_t>(row) * nchunks + c, d);
         }
@@ -121,11 +143,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          gy[i][j] = d[j] * g[j];
-          s1 += gy[i][j];
-          s2 += gy[i][j] * xh[i][j];
-          dg[i][j] += d[j] * xh[i][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float gy = d[j] * g[j];
+          s1 += gy;
+          s2 += gy * xh;
+          dg[i][j] += d[j] * xh;
           db[i][j] += d[j];
         }
       }
@@ -136,9 +158,17 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     for (int i = 0; i < NCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
-        float o[8];
+        float d[8], xv[8], o[8];
+        bf16x8_to_f32(rd[i], d);
+        bf16x8_to_f32(rx[i], xv);
+        if (din.thresh != 0) {
+          drop_apply8(din, static_cast<uint64_t>(row) * nchunks + c, d);  // (regenerated: one LN instance per step)
+        }
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (gy[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * g[j] - s1 - ((xv[j] - mean) * rstd) * s2);
         stg128(dx + off + c * 8, f32_to_bf16x8(o));
         if (dx_drop != nullptr) {
           if (dout.thresh != 0) {
@@ -180,9 +210,24 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restri
   const int r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col0 < cols) {
-    for (int r = r0 + warp; r < r1; r += 8) {
+    // four independent 16-byte loads in flight per lane: with one the short row slices were pure load latency
+    const __nv_bfloat16* xp = x + col0;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = ldg128(xp + static_cast<long long>(r + 8 * u) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        bf16x8_to_f32(q[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+    for (; r < r1; r += 8) {
       float v[8];
-      bf16x8_to_f32(ldg128(x + static_cast<long long>(r) * ld + col0), v);
+      bf16x8_to_f32(ldg128(xp + static_cast<long long>(r) * ld), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }

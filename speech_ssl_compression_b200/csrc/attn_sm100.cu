@@ -39,8 +39,8 @@ struct AttnParams {
   int causal;
   float scale_log2;     // (1/sqrt(64)) * log2(e)
   DropCfg drop;
-  uint8_t* keep;        // optional [B, H, T, keep_pitch]: dropout keep bits (bit i of byte g = key 8g + i), for the backward
-  int keep_pitch;
+  uint32_t* keep;       // optional [B, H, keep_words, T]: dropout keep bits for the backward (bit i of word w of a query row
+  int keep_words;       //   = key 32 w + i); query-minor so that a warp (32 consecutive query rows) writes / reads one line
 };
 
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
@@ -79,7 +79,8 @@ constexpr int FWD_CTAS_PER_SM = FBKV == 64 ? 3 : 2;
 constexpr int FWD_TMEM_COLS = FBKV == 64 ? 128 : 256;
 
 __global__ void __launch_bounds__(192, FWD_CTAS_PER_SM)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV,
+                const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs a 1024-byte aligned base
   uint8_t* sQ = smem;
@@ -106,6 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tm);
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tm_out);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
@@ -222,7 +224,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
       // ---- probabilities, row sum, dropout, bf16 P into swizzled smem
       float l4[4];
       // keep bits of this row's keys (saved for the backward: 1 bit per score instead of a second Philox pass)
-      uint8_t* const keep_row = (use_drop && p.keep != nullptr && q < p.T) ? p.keep + row_id * p.keep_pitch + (k0 >> 3) : nullptr;
+      uint32_t* const keep_row = (use_drop && p.keep != nullptr && q < p.T)
+                                     ? p.keep + ((static_cast<long long>(b) * p.H + h) * p.keep_words + (k0 >> 5)) * p.T + q
+                                     : nullptr;
       const uint64_t drop_base = row_id * groups_per_row + static_cast<uint64_t>(k0 >> 3);
 #pragma unroll 1
       for (int attempt = 0; attempt < 2; ++attempt) {
@@ -269,7 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
             uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
             *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
           }
-          if (keep_row != nullptr) reinterpret_cast<uint32_t*>(keep_row)[c] = kw;
+          if (keep_row != nullptr) keep_row[static_cast<long long>(c) * p.T] = kw;
         }
         const float m_blk = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3])) * sc;
         const bool need = m_blk > m_run + 64.0f;  // (false for m_blk = -inf and for attempt 1)
@@ -295,7 +299,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     }
     // with the keep-scale s folded in: l_run = s * sum(e), O_tmem = s * sum(keep e v)  ->  out = O_tmem * s / l_run
     const float inv = l_run > 0.f ? (use_drop ? p.drop.scale : 1.f) / l_run : 0.f;
-    __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.T + q) * p.E + h * HD;
+    // The bf16 output tile goes through the (now idle) Q buffer and leaves as ONE TMA tile store: per-thread row
+    // stores are 16 bytes per lane into 32 different lines per instruction, which kept the LSU busy for thousands
+    // of cycles per CTA (rows past the sequence end are clipped by the tensor map).
+    const uint32_t o_row = smem_u32(sQ) + r * 128;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
       uint32_t rr[32];
@@ -306,15 +313,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) rr[i] = 0u;
       }
-      if (q < p.T) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float v[8];
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[g * 8 + i]) * inv;
-          stg128(dst + c * 32 + g * 8, f32_to_bf16x8(v));
-        }
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[g * 8 + i]) * inv;
+        sts128(o_row + (((c * 4 + g) ^ (r & 7)) << 4), f32_to_bf16x8(v));
       }
+    }
+    fence_proxy_async_smem();
+    bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tm_out, sQ, h * HD, q0, b);
+      bulk_commit();
+      bulk_wait_read0();  // the CTA may exit (and its shared memory be reused) once the tile has been read
     }
     if (q < p.T)
       p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) - lg_scale : INFINITY;
@@ -364,8 +376,8 @@ struct AttnBwdParams {
   int causal;
   float scale, scale_log2;
   DropCfg drop;
-  const uint8_t* keep;  // [B, H, T, keep_pitch] keep bits written by the forward (required when dropout is on)
-  int keep_pitch;
+  const uint32_t* keep;  // [B, H, keep_words, T] keep bits written by the forward (required when dropout is on)
+  int keep_words;
 };
 
 // smem: K, V (16 KB each) | Q[3], dO[3] (96 KB) | P (32 KB) | dS (32 KB) | dQ staging [128 x 64] f32 (32 KB)
@@ -660,13 +672,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       // addressing is a single 32-bit row index (B H T < 2^31 rows) so the loop carries one register for it
       int srow = (w.b * p.H + w.h) * p.T + w.i_begin * BQ + r;  // (b, h, query) row of this thread in lse / delta / keep
       int q_nx = w.i_begin * BQ + r;
-      const uint8_t* const keep_col = use_drop ? p.keep + ((w.k0 + kc0) >> 3) : nullptr;
+      // keep word of (this thread's 32 keys, query q): base + q, with base = ((b H + h) keep_words + word) T
+      const uint32_t* const keep_col =
+          use_drop ? p.keep + ((static_cast<long long>(w.b) * p.H + w.h) * p.keep_words + ((w.k0 + kc0) >> 5)) * p.T : nullptr;
       if (!pref) {  // (normally fetched during the last query block of the previous item)
         lse_nx = INFINITY; dl_nx = 0.f; kb_nx = 0xffffffffu;
         if (w.n_iter > 0 && q_nx < p.T) {
           lse_nx = __ldg(p.lse + srow);
           dl_nx = __ldg(p.delta + srow);
-          if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+          if (use_drop) kb_nx = __ldg(keep_col + q_nx);
         }
       }
       pref = false;
@@ -702,7 +716,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           if (q_nx < p.T) {
             lse_nx = __ldg(p.lse + srow);
             dl_nx = __ldg(p.delta + srow);
-            if (use_drop) kb_nx = __ldg(reinterpret_cast<const uint32_t*>(keep_col + static_cast<long long>(srow) * p.keep_pitch));
+            if (use_drop) kb_nx = __ldg(keep_col + q_nx);
           }
         } else if (item + static_cast<int>(gridDim.x) < n_items) {
           // last query block: fetch the first block's statistics of the next item (hides the load latency and the
@@ -716,7 +730,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
               lse_nx = __ldg(p.lse + row);
               dl_nx = __ldg(p.delta + row);
               if (use_drop)
-                kb_nx = __ldg(reinterpret_cast<const uint32_t*>(p.keep + ((wn.k0 + kc0) >> 3) + static_cast<long long>(row) * p.keep_pitch));
+                kb_nx = __ldg(p.keep + ((static_cast<long long>(wn.b) * p.H + wn.h) * p.keep_words + ((wn.k0 + kc0) >> 5)) * p.T + q0);
             }
           }
         }
@@ -862,6 +876,9 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   if (rc) return rc;
   rc = make_tmap_3d(&tmkv, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, FBKV);
   if (rc) return rc;
+  CUtensorMap tmo;
+  rc = make_tmap_3d(&tmo, out, E, T, B, E, static_cast<long long>(T) * E, HD, BQ);
+  if (rc) return rc;
   static bool configured = false;
   if (!configured) {
     MH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -872,9 +889,9 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
   p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop(p_drop, seed, site);
-  p.keep = keep_bits;
-  p.keep_pitch = ((T + 127) / 128) * 16;
-  attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, tmkv, p);
+  p.keep = reinterpret_cast<uint32_t*>(keep_bits);
+  p.keep_words = ((T + 127) / 128) * 4;
+  attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, tmkv, tmo, p);
   MH_LAUNCH_CHECK();
   ++g_launches;
   return 0;
@@ -918,8 +935,8 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   p.B = B; p.T = T; p.H = heads; p.E = E; p.causal = causal;
   p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop(p_drop, seed, site);
-  p.keep = keep_bits;
-  p.keep_pitch = ((T + 127) / 128) * 16;
+  p.keep = reinterpret_cast<const uint32_t*>(keep_bits);
+  p.keep_words = ((T + 127) / 128) * 4;
   {
     const long long items = static_cast<long long>((T + BKV - 1) / BKV) * heads * B;
     MH_CHECK(items < (1LL << 31), "attn_bwd: too many work items");

@@ -86,7 +86,7 @@ def _call(name, *args):
 # ------------------------------------------------------------------------------ attention
 def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0, want_keep=True):
     """qkv: bf16 [B*T, 3*64*heads]; kv_len: int32 [B] (or None).
-    Returns (out [B*T, E], lse [B,H,T], keep bits u8 [B,H,T,16*ceil(T/128)] or None when p_drop == 0)."""
+    Returns (out [B*T, E], lse [B,H,T], keep bits (opaque u8 [B,H,T,16*ceil(T/128)] buffer, see mh_b200.h) or None when p_drop == 0)."""
     E = 64 * heads
     if qkv.dtype != bf16 or tuple(qkv.shape) != (B * T, 3 * E) or not qkv.is_contiguous():
         raise ValueError(f"attn_fwd: qkv must be contiguous bf16 [{B * T}, {3 * E}], got {tuple(qkv.shape)}")

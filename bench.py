@@ -202,7 +202,9 @@ def live_gemm_roofline(ts, batch, peaks):
         e0.record()
         r = real(a, b, out, a_mn=a_mn, b_mn=b_mn, epilogue=epilogue, **kw)
         e1.record()
-        rec.append((epilogue, 2.0 * M * N * Kd, e0, e1))
+        # algorithmic operand bytes: A + B read once, every output written once (bf16; fp32 for the wgrad reduce-add)
+        nb = 2.0 * (M * Kd + N * Kd) + (4.0 if epilogue == K.EPI_F32 else 2.0) * M * N
+        rec.append((epilogue, 2.0 * M * N * Kd, e0, e1, nb))
         return r
 
     f, l, p, lens = batch
@@ -220,16 +222,28 @@ def live_gemm_roofline(ts, batch, peaks):
         ts.use_graph = was_graph
     by = {}
     flops = ms = 0.0
-    for epi, fl, e0, e1 in rec:
+    abytes = 0.0
+    for epi, fl, e0, e1, nb in rec:
         t = e0.elapsed_time(e1)
         flops += fl
         ms += t
+        abytes += nb
         d = by.setdefault(names[epi], [0, 0.0, 0.0])
         d[0] += 1; d[1] += fl; d[2] += t
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = flops / ms / 1e9
-    return {"bound": "tensor", "kernel": "mh::gemm_kernel<BN, EPI, A_MN, B_MN> (all tcgen05 GEMM launches of one optimizer step)",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+    # DRAM traffic per launch of the same kernel family, from the committed ncu capture of this command
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return {"bound": "tensor", "kernel": "mh::gemm_pair_kernel<EPI, A_MN, B_MN> / mh::gemm_kernel<BN, ...> (all tcgen05 GEMM launches of one optimizer step)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, average over the family)",
+            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": abytes / max(len(rec), 1),
             "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a running step)" if peaks
                             else "fallback 1.4 PFLOP/s sustained"),
             "launches": len(rec), "gemm_ms_per_step": ms, "gemm_tflop_per_step": flops / 1e12,

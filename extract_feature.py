@@ -31,6 +31,7 @@ def get_args(argv=None):
     ap.add_argument("-f", "--fp", type=int, default=20, help="frame period")
     ap.add_argument("-d", "--hours", type=int, choices=[360, 960], default=960)
     ap.add_argument("--device", default="cuda")
+    ap.add_argument("--host-fbank", action="store_true", help="compute the fbank with torchaudio on the host like the reference")
     ap.add_argument("wavs", nargs="*", help="audio files (default: the two example FLACs)")
     return ap.parse_args(argv)
 
@@ -62,6 +63,25 @@ def extract_fbank(path, mean, std, fp=20):
             even = torch.cat((even, torch.zeros(1, even.shape[1])), dim=0)
         y = torch.cat((odd, even), dim=1)
     return y
+
+
+def prepare_data_gpu(paths, fp=20, hours=360, device="cuda"):
+    """Same tuple as prepare_data with the fbank / normalisation / frame stacking on the GPU (``mh_fbank``): only the
+    FLAC bitstream decode stays on the host."""
+    from speech_ssl_compression_b200.frontend.fbank import kaldi_fbank, stack_frames
+
+    ms = np.load(os.path.join(EXAMPLE, f"libri-{hours}-mean-std.npy"))
+    waves = []
+    for p in paths:
+        wav, sr = load_waveform(p)
+        if sr != 16000:
+            raise RuntimeError(f"{p}: sample rate {sr}, the front-end is built for 16 kHz")
+        waves.append(wav.reshape(-1))
+    feat, frames = kaldi_fbank(waves, ms[0].reshape(-1), ms[1].reshape(-1), device=device)
+    mel, lens = stack_frames(feat, frames, fp)
+    mel = mel[:, : max(lens)].contiguous()
+    pad = (torch.arange(mel.shape[1], device=mel.device)[None, :] < torch.tensor(lens, device=mel.device)[:, None]).float()
+    return mel, lens, pad
 
 
 def prepare_data(paths, fp=20, hours=360):
@@ -107,7 +127,10 @@ def load_model(args):
 def main(argv=None):
     args = get_args(argv)
     paths = args.wavs or [os.path.join(EXAMPLE, "100-121669-0000.flac"), os.path.join(EXAMPLE, "1001-134707-0000.flac")]
-    mel, lens, pad = prepare_data(paths, args.fp, args.hours)
+    if torch.device(args.device).type == "cuda" and not args.host_fbank:
+        mel, lens, pad = prepare_data_gpu(paths, args.fp, args.hours, args.device)
+    else:
+        mel, lens, pad = prepare_data(paths, args.fp, args.hours)
     model = load_model(args)
     with torch.no_grad():
         out = model(mel.to(args.device), pad.to(args.device), get_hidden=True, no_pred=True)

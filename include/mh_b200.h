@@ -235,6 +235,23 @@ int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
                  float beta2, float eps, float weight_decay, const unsigned long long* step /* device, 1-based */, float grad_scale,
                  float max_norm, const float* sumsq, int zero_grad, void* bf16_shadow, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Front-end: batched Kaldi-compatible log-mel filterbank, replacing the host-side
+ * torchaudio.compliance.kaldi.fbank call of extract_feature.py:32-53 and s3prl_upstream/expert.py:23-43
+ * (num_mel_bins=40, sample_frequency=16000, window_type='hamming', frame_length=25, frame_shift=10 on the
+ * waveform x 2^15; torchaudio defaults otherwise: dither 0, preemphasis 0.97, remove_dc_offset, snip_edges,
+ * 512-point FFT, power spectrum, log(max(e, FLT_EPSILON)), no energy) and the (y - mean) / std normalisation
+ * that follows it (extract_feature.py:42-44).
+ *   wave        : f32 [batch, ld_wave] zero-padded waveforms in [-1, 1);  n_samples : i32 [batch]
+ *   mel_weights : f32 [n_mel, 257] (get_mel_banks(...) padded with a zero column, built on the host)
+ *   mean, inv_std : f32 [n_mel] or both NULL;  window_type : 0 hamming, 1 hanning, 2 povey, 3 rectangular
+ *   out         : f32 [batch, max_frames, n_mel]; frame f of utterance b exists for
+ *                 f < 1 + (n_samples[b] - frame_len) / frame_shift, the rest is written as 0.
+ * ------------------------------------------------------------------------------------- */
+int mh_fbank(const float* wave, long long ld_wave, const int* n_samples, int batch, const float* mel_weights,
+             const float* mean, const float* inv_std, float* out, int max_frames, int n_mel, int frame_len,
+             int frame_shift, float scale, float preemph, int window_type, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

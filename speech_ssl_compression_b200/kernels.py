@@ -364,3 +364,27 @@ def set_dropout_offset(counter):
 
 def counter_add(counter, v=1):
     _call("mh_counter_add", _p(counter), c_uint64(v), _s())
+
+
+# ------------------------------------------------------------------------------ front-end
+def fbank(wave, n_samples, mel_weights, *, mean=None, inv_std=None, frame_len=400, frame_shift=160, scale=32768.0,
+          preemph=0.97, window_type=0):
+    """wave: f32 [B, L] zero-padded waveforms; n_samples: int32 [B]; mel_weights: f32 [n_mel, 257].
+    Returns f32 [B, max_frames, n_mel] log-mel features (normalised when mean / inv_std are given), frames past
+    an utterance's end are 0.  ``max_frames`` follows from L (snip_edges)."""
+    if wave.dtype != torch.float32 or wave.dim() != 2 or wave.stride(1) != 1:
+        raise ValueError("fbank: wave must be f32 [B, L] with unit inner stride")
+    if n_samples.dtype != torch.int32 or n_samples.numel() != wave.shape[0]:
+        raise ValueError("fbank: n_samples must be int32 [B]")
+    if mel_weights.dtype != torch.float32 or mel_weights.dim() != 2 or mel_weights.shape[1] != 257 or not mel_weights.is_contiguous():
+        raise ValueError("fbank: mel_weights must be contiguous f32 [n_mel, 257]")
+    B, L_ = wave.shape
+    if L_ < frame_len:
+        raise ValueError(f"fbank: waveforms shorter than one frame ({L_} < {frame_len})")
+    max_frames = 1 + (L_ - frame_len) // frame_shift
+    n_mel = mel_weights.shape[0]
+    out = torch.empty(B, max_frames, n_mel, device=wave.device, dtype=torch.float32)
+    _call("mh_fbank", _p(wave), c_longlong(wave.stride(0)), _p(n_samples), c_int(B), _p(mel_weights), _p(mean), _p(inv_std),
+          _p(out), c_int(max_frames), c_int(n_mel), c_int(frame_len), c_int(frame_shift), _f(scale), _f(preemph),
+          c_int(window_type), _s())
+    return out

@@ -80,3 +80,35 @@ def test_fbank_vs_torchaudio_ragged_batch():
         assert ref.shape[0] == frames[i]
         assert (feat[i, : frames[i]].cpu() - ref).abs().max() < 1e-3   # log-mel, natural log units
         assert float(feat[i, frames[i]:].abs().max()) == 0.0 if frames[i] < feat.shape[1] else True
+
+
+@pytest.mark.gpu
+def test_s3prl_upstream_expert_end_to_end_matches_reference_golden(tmp_path):
+    """Waveforms -> mh_fbank -> encoder through the S3PRL-style expert (s3prl_upstream/expert.py:113-139) against the
+    golden of the reference's extract_feature.py on the same FLACs and the same random-init (seed 1337) weights."""
+    import random
+
+    import extract_feature as EF
+    from speech_ssl_compression_b200.model import MelHuBERTConfig, MelHuBERTModel
+    from speech_ssl_compression_b200.s3prl_upstream import UpstreamExpert
+
+    g = np.load(os.path.join(GOLD, "extract_cfg1.npz"))
+    random.seed(1337); np.random.seed(1337); torch.manual_seed(1337)
+    cfg = dict(feat_emb_dim=80, encoder_layers=12, mask_prob=0.7, mask_length=5)
+    m = MelHuBERTModel(MelHuBERTConfig(cfg))
+    ckpt = str(tmp_path / "random_init.ckpt")
+    torch.save({"Upstream_Config": {"melhubert": cfg}, "model": m.state_dict()}, ckpt)
+    ex = UpstreamExpert(ckpt, mode="melhubert", fp=20, mean_std_npy_path=os.path.join(EXAMPLE, "libri-960-mean-std.npy"))
+    ex = ex.to("cuda").eval()
+    assert ex.get_downsample_rates("hidden_states") == 320
+    wavs = [EF.load_waveform(p)[0].reshape(-1).to("cuda") for p in PATHS]
+    with torch.no_grad():
+        st = ex(wavs)
+    assert set(st) == {"hidden_states", "last_hidden_state"} and len(st["hidden_states"]) == 13
+    assert tuple(st["last_hidden_state"].shape) == tuple(int(x) for x in g["shape"])
+    got = st["last_hidden_state"][:, ::7, ::16].float().cpu().numpy()
+    want = g["hidden"]
+    rel = np.linalg.norm(got[1] - want[1]) / np.linalg.norm(want[1])
+    assert rel < 2.5e-2, rel      # bf16 pipeline vs the fp32 reference (DESIGN.md section 4)
+    with pytest.raises(RuntimeError):
+        ex([w.cpu() for w in wavs])

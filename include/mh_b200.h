@@ -77,8 +77,9 @@ int mh_gemm(const mh_gemm_args* args, void* stream);
 int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, uint8_t* keep_bits, int B, int T, int heads,
                 int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
 /* keep_bits : 16 * ceil(T / 128) bytes per (batch, head, query) = u32 [B, heads, 4 * ceil(T / 128), T] -- the dropout
- *   decisions of the forward (bit i of word w of a query row = key 32 w + i; query-minor so that 32 consecutive
- *   query rows share a 128-byte line), written by mh_attn_fwd when non-NULL and p_drop > 0 and REQUIRED by
+ *   decisions of the forward (word w of a query row covers keys 32 w .. 32 w + 31, key 8 g + 2 j + h of them in bit
+ *   15 + 16 h - j - 4 g: the order the forward's predicate-free compare produces them in; query-minor so that 32
+ *   consecutive query rows share a 128-byte line; opaque to callers), written by mh_attn_fwd when non-NULL and p_drop > 0 and REQUIRED by
  *   mh_attn_bwd when p_drop > 0 (1 bit per score instead of re-running Philox in the instruction-bound backward).
  * dqkv : bf16 [B*T, 3*E];  delta : f32 scratch [B, heads, T];  dq_acc : f32 scratch [B*T, E] */
 int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,

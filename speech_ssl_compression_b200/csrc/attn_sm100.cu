@@ -39,8 +39,8 @@ struct AttnParams {
   int causal;
   float scale_log2;     // (1/sqrt(64)) * log2(e)
   DropCfg drop;
-  uint32_t* keep;       // optional [B, H, keep_words, T]: dropout keep bits for the backward (bit i of word w of a query row
-  int keep_words;       //   = key 32 w + i); query-minor so that a warp (32 consecutive query rows) writes / reads one line
+  uint32_t* keep;       // optional [B, H, keep_words, T]: dropout keep bits for the backward (word w of a query row = keys
+  int keep_words;       //   32 w .. 32 w + 31, bit order keep_bit_pos()); query-minor so that a warp (32 consecutive query rows) writes / reads one line
 };
 
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
@@ -50,6 +50,19 @@ __device__ __forceinline__ uint32_t swz(int r, int ch) { return r * 128 + ((ch ^
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+
+// Attention-probability dropout without predicates (the forward's softmax loop is instruction-bound).  The 128 Philox
+// bits of a group of 8 keys are eight 16-bit lanes; the low 15 bits of lane e are compared with thr15 = round(p 2^15):
+//   y = (w & 0x7fff7fff) + (0x8000 - thr15) * 0x00010001   ->  bit 15 / 31 of y = keep flag of the low / high lane.
+// prmt with sign replication turns the two flags into the 0xffff masks of the packed bf16 pair (1 instruction), and
+// the four words' flags are OR-ed, shifted by their word index, into one keep word per 32 keys:
+//   key e = 8 g + 2 j + h of a 32-key chunk  ->  bit 15 + 16 h - j - 4 g.
+__device__ __forceinline__ uint32_t sign_mask2(uint32_t y) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"(y));
+  return m;
+}
+__host__ __device__ constexpr int keep_bit_pos(int e) { return 15 + 16 * (e & 1) - ((e & 7) >> 1) - 4 * (e >> 3); }
 
 // rare path of the forward softmax (lazy rescaling): kept out of line so the hot loop stays small
 __device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
@@ -180,6 +193,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     const float sc = p.scale_log2;
     const bool use_drop = p.drop.thresh != 0;
     const DropState ds(p.drop);
+    const uint32_t drop_add = (0x8000u - ((p.drop.thresh + 1u) >> 1)) * 0x00010001u;  // see sign_mask2
     // the dropout keep-scale 1/(1-p) is folded into the exponent: probabilities (and the running row sum)
     // carry the constant factor, which the final normalisation and the saved log-sum-exp divide out again
     const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
@@ -258,20 +272,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
                                              fmaxf(__uint_as_float(rr[g * 8 + 6]), __uint_as_float(rr[g * 8 + 7])))));
             // pairwise tree + four accumulators: no long dependent FADD chain
             l4[g] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+            uint4 pw = f32_to_bf16x8(pv);
             if (use_drop) {
               const uint4 bits = ds.bits(drop_base + (c * 4 + g));
-              uint32_t kb = 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const bool k = ds.keep(bits, i);
-                pv[i] = k ? pv[i] : 0.f;
-                kb |= static_cast<uint32_t>(k) << i;
-              }
-              kw |= kb << (8 * g);
+              const uint32_t y0 = (bits.x & 0x7fff7fffu) + drop_add, y1 = (bits.y & 0x7fff7fffu) + drop_add;
+              const uint32_t y2 = (bits.z & 0x7fff7fffu) + drop_add, y3 = (bits.w & 0x7fff7fffu) + drop_add;
+              pw.x &= sign_mask2(y0); pw.y &= sign_mask2(y1); pw.z &= sign_mask2(y2); pw.w &= sign_mask2(y3);
+              const uint32_t t = (y0 & 0x80008000u) | ((y1 & 0x80008000u) >> 1) | ((y2 & 0x80008000u) >> 2) |
+                                 ((y3 & 0x80008000u) >> 3);
+              kw |= t >> (4 * g);
             }
             const int kc = c * 32 + g * 8;  // key column inside the block
             uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
-            *reinterpret_cast<uint4*>(dst) = f32_to_bf16x8(pv);
+            *reinterpret_cast<uint4*>(dst) = pw;
           }
           if (keep_row != nullptr) keep_row[static_cast<long long>(c) * p.T] = kw;
         }
@@ -768,8 +781,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
               uint32_t w4[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const uint32_t two = kbits >> (8 * g + 2 * t);
-                const uint32_t m = ((two & 1u) ? 0x0000ffffu : 0u) | ((two & 2u) ? 0xffff0000u : 0u);
+                const uint32_t m = (((kbits >> keep_bit_pos(8 * g + 2 * t)) & 1u) ? 0x0000ffffu : 0u) |
+                                   (((kbits >> keep_bit_pos(8 * g + 2 * t + 1)) & 1u) ? 0xffff0000u : 0u);
                 w4[t] = pk[4 * g + t] & m;
               }
               sts128(p_row + (((ch0 + g) ^ (r & 7)) << 4), make_uint4(w4[0], w4[1], w4[2], w4[3]));
@@ -797,7 +810,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
               const uint32_t raw = (g & 1) ? db[t] : da[t];
-              const float u = ((kbits >> (8 * g + t)) & 1u) ? __uint_as_float(raw) : 0.f;
+              const float u = ((kbits >> keep_bit_pos(8 * g + t)) & 1u) ? __uint_as_float(raw) : 0.f;
               const uint32_t pw = pk[4 * g + (t >> 1)];
               ds[t] = ((t & 1) ? bf16_hi(pw) : bf16_lo(pw)) * fmaf(u, p.scale, -dls);
             }

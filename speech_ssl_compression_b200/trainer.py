@@ -153,6 +153,68 @@ class TrainStep:
         self.h2d_bytes = nbytes
         self._lens = list(lens)
 
+    # ---- input pipelining (no host work or sync between steps): the next batch is drawn / copied
+    #      while the current step runs, the loss is read back one step late
+    def stage_batch(self, feat, label, pad, lens, masking=True):
+        """Asynchronous ``load_batch``: the host->device copies (pinned memory) go to STAGING buffers on a copy
+        stream, so they and the host-side span-mask draw overlap the step in flight; ``commit_staged`` moves
+        them into the step's static input buffers.  Call it AFTER ``run`` of the previous step (the NumPy
+        stream must see mask draw, layer-drop draws, mask draw, ... in the reference's order)."""
+        if not hasattr(self, "_cs"):
+            dev = self.device
+            self._cs = torch.cuda.Stream(device=dev)
+            self._s_feat, self._s_label = torch.empty_like(self.feat), torch.empty_like(self.label)
+            self._s_pad, self._s_mask = torch.empty_like(self.pad), torch.empty_like(self.mask)
+            self._h_masks = [torch.zeros(self.B, self.T, dtype=torch.bool).pin_memory() for _ in range(2)]
+            self._staged_ev, self._commit_ev = torch.cuda.Event(), torch.cuda.Event()
+            self._commit_ev.record()
+            self._stage_i = 0
+        hm = self._h_masks[self._stage_i & 1]
+        self._stage_i += 1
+        if masking:
+            hm.copy_(torch.from_numpy(self.draw_mask(lens)))  # (its previous copy, two stages ago, has long landed)
+        self._cs.wait_event(self._commit_ev)  # the previous commit has read the staging buffers
+        with torch.cuda.stream(self._cs):
+            self._s_feat.copy_(feat, non_blocking=True)
+            self._s_label.copy_(label, non_blocking=True)
+            self._s_pad.copy_(pad, non_blocking=True)
+            if masking:
+                self._s_mask.copy_(hm, non_blocking=True)
+            self._staged_ev.record()
+        self._staged = (feat.numel() * 4 + label.numel() * 8 + pad.numel() * 4 + (hm.numel() if masking else 0),
+                        list(lens), masking)
+
+    def commit_staged(self):
+        """Device-to-device copy of the staged batch into the step's input buffers (current stream)."""
+        nbytes, lens, masking = self._staged
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged_ev)
+        self.feat.copy_(self._s_feat, non_blocking=True)
+        self.label.copy_(self._s_label, non_blocking=True)
+        self.pad.copy_(self._s_pad, non_blocking=True)
+        if masking:
+            self.mask.copy_(self._s_mask, non_blocking=True)
+        self._commit_ev.record(cur)
+        self.h2d_bytes, self._lens = nbytes, lens
+
+    def read_loss_async(self):
+        """Queue the device->host copy of this step's loss; returns a handle for ``collect_loss``."""
+        if not hasattr(self, "_h_losses"):
+            self._h_losses = [(torch.zeros(1).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._loss_i = 0
+        buf, ev = self._h_losses[self._loss_i & 3]
+        self._loss_i += 1
+        buf.copy_(self.loss, non_blocking=True)
+        ev.record()
+        self.d2h_bytes = 4
+        return buf, ev
+
+    @staticmethod
+    def collect_loss(handle):
+        buf, ev = handle
+        ev.synchronize()
+        return float(buf[0])
+
     def _body(self):
         K.counter_add(self.rng_counter, 1)
         data = (self.feat, self.label, self.pad, None)

@@ -399,6 +399,53 @@ def test_distillation_l1cos_vs_oracle():
 
 
 # ------------------------------------------------------------------------------- train-step driver
+def test_train_step_pipelined_inputs_equal_blocking_loads():
+    """stage_batch / commit_staged / read_loss_async (next batch drawn and copied while the step runs, loss read one
+    step late) feed the step exactly what load_batch / read_loss do: same span masks (same NumPy stream order),
+    same batches, same loss trajectory."""
+    from speech_ssl_compression_b200.trainer import TrainStep
+    from speech_ssl_compression_b200.upstream.melhubert.pretrain_expert import MelHuBERTPretrainer
+
+    cfg = base_cfg(20, 2)
+    B, T, D = 2, 256, 80
+    batches = []
+    for seed, lens in ((8, [256, 200]), (9, [256, 131])):
+        f, l, p = O.synth_batch(B, T, D, lens, seed=seed)
+        batches.append((f.pin_memory(), l.pin_memory(), p.pin_memory(), lens))
+    losses, masks = {}, {}
+    for piped in (False, True):
+        torch.manual_seed(5)
+        ex = MelHuBERTPretrainer({"melhubert": dict(cfg)}, None, DEV, False).to(DEV).train()
+        ts = TrainStep(ex, B, T, D, lr=1e-4, max_norm=10.0, use_graph=False)
+        np.random.seed(11)
+        out, ms = [], []
+        if not piped:
+            for i in range(5):
+                ts.load_batch(*batches[i % 2])
+                ts.run()
+                ms.append(ts.mask.clone())
+                out.append(ts.read_loss())
+        else:
+            ts.stage_batch(*batches[0])
+            pending = None
+            for i in range(5):
+                ts.commit_staged()
+                ts.run()
+                ms.append(ts.mask.clone())
+                h = ts.read_loss_async()
+                if i + 1 < 5:
+                    ts.stage_batch(*batches[(i + 1) % 2])
+                if pending is not None:
+                    out.append(ts.collect_loss(pending))
+                pending = h
+            out.append(ts.collect_loss(pending))
+            assert ts.h2d_bytes == B * T * (D * 4 + 8 + 4 + 1) and ts.d2h_bytes == 4
+        losses[piped], masks[piped] = out, ms
+    for a, b in zip(masks[False], masks[True]):
+        assert torch.equal(a, b)
+    np.testing.assert_allclose(losses[True], losses[False], rtol=2e-3)
+
+
 def test_train_step_graph_equals_eager():
     """trainer.TrainStep: the CUDA-graph-captured optimizer step produces the same loss
     trajectory as the eager step (dropout 0), and the loss goes down."""

@@ -120,7 +120,6 @@ class TrainStep:
         self.pad = torch.ones(B, T, device=dev)
         self.mask = torch.zeros(B, T, device=dev, dtype=torch.bool)
         self.loss = torch.zeros(1, device=dev)
-        self.h_mask = torch.zeros(B, T, dtype=torch.bool).pin_memory()
         self.h_loss = torch.zeros(1).pin_memory()
         self.rng_counter = torch.zeros(1, device=dev, dtype=torch.int64)
         K.set_dropout_offset(self.rng_counter)
@@ -141,17 +140,11 @@ class TrainStep:
         return m
 
     def load_batch(self, feat, label, pad, lens, masking=True):
-        """feat / label / pad: pinned host tensors.  Copies are asynchronous on the current stream."""
-        self.feat.copy_(feat, non_blocking=True)
-        self.label.copy_(label, non_blocking=True)
-        self.pad.copy_(pad, non_blocking=True)
-        nbytes = feat.numel() * 4 + label.numel() * 8 + pad.numel() * 4
-        if masking:
-            self.h_mask.copy_(torch.from_numpy(self.draw_mask(lens)))
-            self.mask.copy_(self.h_mask, non_blocking=True)
-            nbytes += self.h_mask.numel()
-        self.h2d_bytes = nbytes
-        self._lens = list(lens)
+        """feat / label / pad: pinned host tensors.  ``stage_batch`` + ``commit_staged`` in one call: the copies are
+        asynchronous, and the pinned span-mask buffers are only rewritten once their previous copy has run -- a
+        training loop that never synchronises may be several steps ahead of the GPU."""
+        self.stage_batch(feat, label, pad, lens, masking)
+        self.commit_staged()
 
     # ---- input pipelining (SURVEY 8 f-2: no host work or sync between steps): the next batch is drawn / copied
     #      while the current step runs, the loss is read back one step late
@@ -166,13 +159,17 @@ class TrainStep:
             self._s_feat, self._s_label = torch.empty_like(self.feat), torch.empty_like(self.label)
             self._s_pad, self._s_mask = torch.empty_like(self.pad), torch.empty_like(self.mask)
             self._h_masks = [torch.zeros(self.B, self.T, dtype=torch.bool).pin_memory() for _ in range(2)]
+            self._h_mask_ev = [torch.cuda.Event(), torch.cuda.Event()]
             self._staged_ev, self._commit_ev = torch.cuda.Event(), torch.cuda.Event()
             self._commit_ev.record()
             self._stage_i = 0
-        hm = self._h_masks[self._stage_i & 1]
+        k = self._stage_i & 1
+        hm = self._h_masks[k]
         self._stage_i += 1
         if masking:
-            hm.copy_(torch.from_numpy(self.draw_mask(lens)))  # (its previous copy, two stages ago, has long landed)
+            m = self.draw_mask(lens)
+            self._h_mask_ev[k].synchronize()  # the copy that last read this pinned buffer (two stages ago) has run
+            hm.copy_(torch.from_numpy(m))
         self._cs.wait_event(self._commit_ev)  # the previous commit has read the staging buffers
         with torch.cuda.stream(self._cs):
             self._s_feat.copy_(feat, non_blocking=True)
@@ -180,6 +177,7 @@ class TrainStep:
             self._s_pad.copy_(pad, non_blocking=True)
             if masking:
                 self._s_mask.copy_(hm, non_blocking=True)
+                self._h_mask_ev[k].record()
             self._staged_ev.record()
         self._staged = (feat.numel() * 4 + label.numel() * 8 + pad.numel() * 4 + (hm.numel() if masking else 0),
                         list(lens), masking)

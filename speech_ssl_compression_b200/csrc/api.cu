@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by all kernel files: error string, SM count, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mh_b200.h"
@@ -20,6 +21,15 @@ static const unsigned long long* g_drop_offset = nullptr;
 const unsigned long long* dropout_offset_ptr() { return g_drop_offset; }
 
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long v) { *c += v; }
+
+bool pdl_enabled(int family) {  // MH_PDL: bit mask of kernel families (1 GEMM, 2 attention, 4 norm / column sums)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MH_PDL");
+    on = e == nullptr ? 3 : atoi(e);  // (measured: +0.1 ms each for GEMM and attention, -0.56 ms for the many-CTA norm kernels)
+  }
+  return (on & family) != 0;
+}
 
 int sm_count() {
   static int n = 0;

@@ -17,6 +17,7 @@
 //   dV += P_drop^T dO, dK += dS^T Q (MN-major A and B operands, accumulating in TMEM across
 //   the whole query loop) and dQ_i = dS K (red.global.add.f32 into an fp32 workspace).
 #include "mh_b200.h"
+#define MH_PDL_FAMILY 2
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
 
@@ -94,6 +95,7 @@ constexpr int FWD_TMEM_COLS = FBKV == 64 ? 128 : 256;
 __global__ void __launch_bounds__(192, FWD_CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs a 1024-byte aligned base
   uint8_t* sQ = smem;
@@ -355,6 +357,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                   int B, int T, int H) {
+  pdl_prologue();
   const long long total = static_cast<long long>(B) * T * H * 8;  // 16-byte chunks
   for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < ((total + 31) & ~31LL);
        c += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -419,6 +422,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tm_dkv,
                 const AttnBwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -863,6 +867,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
 // dqkv[:, 0:E] = bf16(dq_acc)
 __global__ void dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, long long rows, int E) {
+  pdl_prologue();
   const int cpr = E >> 3;
   const long long total = rows * cpr;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -904,8 +909,7 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   p.drop = make_drop(p_drop, seed, site);
   p.keep = reinterpret_cast<uint32_t*>(keep_bits);
   p.keep_words = ((T + 127) / 128) * 4;
-  attn_fwd_kernel<<<dim3((T + BQ - 1) / BQ, heads, B), 192, FWD_SMEM, st>>>(tm, tmkv, tmo, p);
-  MH_LAUNCH_CHECK();
+  MH_CUDA(launch_pdl(attn_fwd_kernel, dim3((T + BQ - 1) / BQ, heads, B), dim3(192), FWD_SMEM, st, tm, tmkv, tmo, p));
   ++g_launches;
   return 0;
 }
@@ -937,11 +941,11 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   const long long pairs = rows * heads;
   long long dgrid = (pairs * 8 + 255) / 256;
   if (dgrid > static_cast<long long>(sm_count()) * 16) dgrid = static_cast<long long>(sm_count()) * 16;
-  attn_delta_kernel<<<static_cast<int>(dgrid), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T, heads);
-  MH_LAUNCH_CHECK();
+  MH_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * E, st));  // (first: the kernels below chain through PDL)
+  MH_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(dgrid)), dim3(256), 0, st,
+                     reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T,
+                     heads));
   ++g_launches;
-  MH_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * E, st));
   AttnBwdParams p;
   p.kv_len = kv_len; p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
@@ -954,15 +958,15 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
     const long long items = static_cast<long long>((T + BKV - 1) / BKV) * heads * B;
     MH_CHECK(items < (1LL << 31), "attn_bwd: too many work items");
     const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
-    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq, tdo, tdq, tdkv, p);
+    MH_CUDA(launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, st, tq, tdo, tdq, tdkv, p));
   }
   MH_LAUNCH_CHECK();
   ++g_launches;
   long long g = (rows * (E / 8) + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (g > cap) g = cap;
-  dq_finish_kernel<<<static_cast<int>(g), 256, 0, st>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), rows, E);
-  MH_LAUNCH_CHECK();
+  MH_CUDA(launch_pdl(dq_finish_kernel, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, static_cast<const float*>(dq_acc),
+                     reinterpret_cast<__nv_bfloat16*>(dqkv), rows, E));
   ++g_launches;
   return 0;
 }

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "mh_b200.h"
+#define MH_PDL_FAMILY 1
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
 
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
             const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
+  pdl_prologue();
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -483,6 +485,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
                  const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
+  pdl_prologue();
   constexpr int BN = G2_BN;
   extern __shared__ uint8_t smem_raw[];
   // identical offsets in both CTAs (the dynamic smem base is the same for every CTA of a launch)
@@ -696,8 +699,7 @@ static int launch(const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st
     MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::kSmemBytes));
     configured = true;
   }
-  kfn<<<grid, GEMM_THREADS, TileCfg<BN>::kSmemBytes, st>>>(t.a, t.b, t.d, t.aux_in, t.aux_out, d);
-  MH_LAUNCH_CHECK();
+  MH_CUDA(launch_pdl(kfn, dim3(grid), dim3(GEMM_THREADS), TileCfg<BN>::kSmemBytes, st, t.a, t.b, t.d, t.aux_in, t.aux_out, d));
   ++g_launches;
   return 0;
 }
@@ -710,8 +712,7 @@ static int launch_pair(const GemmMaps& t, const GemmDev& d, int grid, cudaStream
     MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
     configured = true;
   }
-  kfn<<<grid, GEMM_THREADS, G2_SMEM, st>>>(t.a, t.b, t.d, t.aux_in, t.aux_out, d);
-  MH_LAUNCH_CHECK();
+  MH_CUDA(launch_pdl(kfn, dim3(grid), dim3(GEMM_THREADS), G2_SMEM, st, t.a, t.b, t.d, t.aux_in, t.aux_out, d));
   ++g_launches;
   return 0;
 }

@@ -29,6 +29,33 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 
+// ---- programmatic dependent launch (PDL) ----
+// A step is ~320 short kernels: the launch gap + prologue of every one of them (1.0 of 21.4 ms) sat exposed on
+// the stream.  Kernels launched through launch_pdl() may be scheduled while the previous kernel of the stream is
+// still draining; EVERY such kernel executes pdl_prologue() before it touches global memory (griddepcontrol.wait:
+// all prerequisite grids complete and their writes visible), so only launch latency, CTA scheduling and the
+// instructions in front of the wait overlap the predecessor's tail.  MH_PDL (bit mask of kernel families, default 3 = GEMM + attention) selects who is launched this way; 0 restores plain launches.
+bool pdl_enabled(int family = 1);
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_f(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(family) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define launch_pdl(...) launch_pdl_f(MH_PDL_FAMILY, __VA_ARGS__)
+
 // ---- Philox4x32-7 (Salmon et al., SC'11: 7 rounds is the smallest crush-resistant variant) ----
 // One 32x32->64 multiply per half round (IMAD.WIDE), round keys on the uniform datapath.
 struct Philox {

@@ -2,6 +2,7 @@
 // per row, 16-byte loads, fp32 statistics, warp-shuffle reductions, no shared-memory staging
 // of the row (each element is touched once).
 #include "mh_b200.h"
+#define MH_PDL_FAMILY 4
 #include "mh_common.cuh"
 
 namespace mh {
@@ -15,6 +16,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
               int cols, float eps, DropCfg drop) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * LN_WARPS;
@@ -89,6 +91,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma,
               float* __restrict__ dbeta, int rows, int cols, DropCfg din, DropCfg dout) {
+  pdl_prologue();
   __shared__ float red[LN_WARPS][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -203,6 +206,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int rows, int cols,
               int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col0 = blockIdx.x * 256 + lane * 8;
@@ -267,10 +271,9 @@ extern "C" int mh_layernorm_fwd(const void* x, const float* gamma, const float* 
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * 8);
   const DropCfg d = make_drop(p_drop, seed, site);
   return dispatch_nch(cols, [&](auto nch) {
-    ln_fwd_kernel<decltype(nch)::value><<<grid, LN_WARPS * 32, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, rows,
-        cols, eps, d);
-    MH_LAUNCH_CHECK();
+    MH_CUDA(launch_pdl(ln_fwd_kernel<decltype(nch)::value>, dim3(grid), dim3(LN_WARPS * 32), 0, st,
+                       reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd,
+                       rows, cols, eps, d));
     ++g_launches;
     return 0;
   });
@@ -285,11 +288,10 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_BWD_GRID_MULT);
   const DropCfg din = make_drop(p_in, seed_in, site_in), dout = make_drop(p_out, seed_out, site_out);
   return dispatch_nch(cols, [&](auto nch) {
-    ln_bwd_kernel<decltype(nch)::value><<<grid, LN_WARPS * 32, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
-        reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows, cols,
-        din, dout);
-    MH_LAUNCH_CHECK();
+    MH_CUDA(launch_pdl(ln_bwd_kernel<decltype(nch)::value>, dim3(grid), dim3(LN_WARPS * 32), 0, st,
+                       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
+                       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows,
+                       cols, din, dout));
     ++g_launches;
     return 0;
   });
@@ -303,8 +305,8 @@ extern "C" int mh_colsum(const void* x, long long ld, float* out, int rows, int 
   int rpb = (rows + gy - 1) / gy;
   if (rpb < 64) rpb = 64;
   gy = (rows + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows, cols, rpb);
-  MH_LAUNCH_CHECK();
+  MH_CUDA(launch_pdl(colsum_kernel, dim3(gx, gy), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows,
+                     cols, rpb));
   ++g_launches;
   return 0;
 }

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
             const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
-  pdl_prologue();
+  pdl_launch_dependents();  // (pdl_wait() follows the set-up below: nothing in front of it reads global memory)
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -330,6 +330,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  pdl_wait();  // barriers initialised, TMEM allocated, descriptors prefetched under the previous kernel's tail
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -485,7 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAuxIn,
                  const __grid_constant__ CUtensorMap tmAuxOut, const GemmDev p) {
-  pdl_prologue();
+  pdl_launch_dependents();  // (pdl_wait() follows the set-up below: nothing in front of it reads global memory)
   constexpr int BN = G2_BN;
   extern __shared__ uint8_t smem_raw[];
   // identical offsets in both CTAs (the dynamic smem base is the same for every CTA of a launch)
@@ -527,6 +528,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  pdl_wait();  // barriers initialised, TMEM allocated, descriptors prefetched under the previous kernel's tail
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

@@ -30,15 +30,19 @@ void set_error(const char* fmt, ...);
 int sm_count();
 
 // ---- programmatic dependent launch (PDL) ----
-// A step is ~320 short kernels: the launch gap + prologue of every one of them (1.0 of 21.4 ms) sat exposed on
-// the stream.  Kernels launched through launch_pdl() may be scheduled while the previous kernel of the stream is
-// still draining; EVERY such kernel executes pdl_prologue() before it touches global memory (griddepcontrol.wait:
-// all prerequisite grids complete and their writes visible), so only launch latency, CTA scheduling and the
-// instructions in front of the wait overlap the predecessor's tail.  MH_PDL (bit mask of kernel families, default 3 = GEMM + attention) selects who is launched this way; 0 restores plain launches.
+// A step is ~320 short kernels and ~1.0 of its 21.4 ms is launch gap.  Kernels launched through launch_pdl() may be
+// scheduled while the previous kernel of the stream is still draining; every such kernel executes
+// griddepcontrol.wait (all prerequisite grids complete, their writes visible) before it touches global memory, so
+// launch latency, CTA scheduling and the set-up in front of the wait can overlap the predecessor's tail.
+// MEASURED (bench.py, 1 x B200, CUDA graph): neutral for the GEMM and attention kernels (21.40 vs 21.34 ms per step,
+// within box-to-box noise), 0.56 ms SLOWER for the many-small-CTA norm kernels -- the graph already hides most of the
+// launch latency.  Hence off by default; MH_PDL = bit mask of kernel families (1 GEMM, 2 attention, 4 norm).
 bool pdl_enabled(int family = 1);
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_launch_dependents();
+  pdl_wait();
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl_f(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

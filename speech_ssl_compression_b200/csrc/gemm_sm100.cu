@@ -172,6 +172,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   uint4 held0[4], held1[4];
   // dropout stream position of this thread's row (element (row, col) lives in group row * N/8 + col/8)
   const uint64_t drop_base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + static_cast<uint64_t>(n0 >> 3);
+  const DropState dstate(p.drop);  // (device step counter: one L1-resident load per tile)
   if (active) {
     auto sub_chunk = [&](int s) {
       const int col_in_tile = e.grp * CG + s * 32;
@@ -212,7 +213,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
         }
         if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
-          if (p.drop.thresh != 0) drop_apply8(p.drop, drop_base + ((col_in_tile + q * 8) >> 3), v);
+          if (p.drop.thresh != 0) dstate.apply8(p.drop, drop_base + ((col_in_tile + q * 8) >> 3), v);
         }
         if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
           float a[8];

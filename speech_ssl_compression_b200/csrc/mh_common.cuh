@@ -1,5 +1,5 @@
 // Shared helpers for all kernels: error plumbing for the C ABI, the counter-based dropout
-// RNG (Philox4x32-10), fp32 erf-GELU, small vector load/store helpers.
+// RNG (Philox4x32-7), fp32 erf-GELU, small vector load/store helpers.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -61,32 +61,20 @@ inline cudaError_t launch_pdl_f(int family, void (*kernel)(KArgs...), dim3 grid,
 #define launch_pdl(...) launch_pdl_f(MH_PDL_FAMILY, __VA_ARGS__)
 
 // ---- Philox4x32-7 (Salmon et al., SC'11: 7 rounds is the smallest crush-resistant variant) ----
-// One 32x32->64 multiply per half round (IMAD.WIDE), round keys on the uniform datapath.
-struct Philox {
-  uint32_t k0, k1;
-  __device__ __forceinline__ Philox(uint64_t seed) : k0(static_cast<uint32_t>(seed)), k1(static_cast<uint32_t>(seed >> 32)) {}
-  __device__ __forceinline__ uint4 operator()(uint64_t ctr, uint32_t stream) const {
-    uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = stream, c3 = 0x9E3779B9u;
-    uint32_t a = k0, b = k1;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
-      const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
-      const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ a, n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ b;
-      c1 = static_cast<uint32_t>(p1); c3 = static_cast<uint32_t>(p0);
-      c0 = n0; c2 = n2;
-      a += 0x9E3779B9u; b += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-  }
-};
-
-// Dropout over a logical element stream.  One Philox call covers 8 consecutive elements
-// (eight 16-bit lanes); element e is kept iff lane(e) >= thresh, thresh = round(p * 65536).
-// The forward and the backward regenerate identical decisions from (seed, site, index).
+// Dropout over a logical element stream.  One Philox call covers 8 consecutive elements (eight 16-bit lanes, low
+// half of each word first); element e is kept iff lane(e) >= thresh, thresh = round(p * 65536).  The forward and
+// the backward regenerate identical decisions from (seed, device step counter, site, element / 8):
+//   key     = seed                      -> the 7 round-key pairs are computed ON THE HOST (make_drop) and travel in
+//                                          the kernel parameters: they are constant-bank operands of the LOP3s, no
+//                                          registers and no per-call key schedule
+//   counter = (group_lo, group_hi ^ step_lo, site, 0x9E3779B9 ^ step_hi); `step` is the optional device counter
+//             (CUDA-graph replays advance it), read once per thread (DropState).
+// A call is 14 IMAD.WIDE + 14 LOP3 (+1) for 8 decisions.  (The first version folded the device counter into the
+// KEY: every call re-derived the key schedule and re-read the counter, ~100 instructions per 8 elements, 45 % of
+// the instruction-bound GELU / dropout GEMM epilogues and a third of the LayerNorm backward.)
 struct DropCfg {
-  uint64_t seed;
-  const unsigned long long* offset;  // optional device counter added to the seed (CUDA-graph replays)
+  uint32_t ka[7], kb[7];             // Philox round keys: ka[r] = seed_lo + r * 0x9E3779B9, kb[r] = seed_hi + r * 0xBB67AE85
+  const unsigned long long* offset;  // optional device step counter (CUDA-graph replays)
   uint32_t site;    // unique per dropout site (layer * 8 + site id)
   uint32_t thresh;  // 0 => dropout disabled
   float scale;      // 1 / (1 - p)
@@ -94,7 +82,8 @@ struct DropCfg {
 const unsigned long long* dropout_offset_ptr();
 __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
   DropCfg d;
-  d.seed = seed;
+  uint32_t a = static_cast<uint32_t>(seed), b = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 7; ++r) { d.ka[r] = a; d.kb[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
   d.offset = dropout_offset_ptr();
   d.site = site;
   d.thresh = p > 0.f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u;
@@ -102,70 +91,55 @@ __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   return d;
 }
-// keep-mask bits for the 8 elements [8*group, 8*group+8)
-__device__ __forceinline__ uint32_t drop_keep8(const DropCfg& d, uint64_t group) {
-  const uint64_t seed = d.seed + (d.offset != nullptr ? 0x9E3779B97F4A7C15ull * __ldg(d.offset) : 0ull);
-  uint4 r = Philox(seed)(group, d.site);
-  uint32_t m = 0;
-  m |= ((r.x & 0xFFFFu) >= d.thresh) << 0;
-  m |= ((r.x >> 16) >= d.thresh) << 1;
-  m |= ((r.y & 0xFFFFu) >= d.thresh) << 2;
-  m |= ((r.y >> 16) >= d.thresh) << 3;
-  m |= ((r.z & 0xFFFFu) >= d.thresh) << 4;
-  m |= ((r.z >> 16) >= d.thresh) << 5;
-  m |= ((r.w & 0xFFFFu) >= d.thresh) << 6;
-  m |= ((r.w >> 16) >= d.thresh) << 7;
-  return m;
-}
 
-// the 128 random bits behind drop_keep8 (lane j of the group = 16-bit field j, low half first)
-__device__ __forceinline__ uint4 drop_bits8(const DropCfg& d, uint64_t group) {
-  const uint64_t seed = d.seed + (d.offset != nullptr ? 0x9E3779B97F4A7C15ull * __ldg(d.offset) : 0ull);
-  return Philox(seed)(group, d.site);
-}
-// v[j] = keep_j ? v[j] * scale : 0 for the 8 elements of `group`, without materialising the bit mask:
-// the high field is compared in place (word >= thresh << 16), the low one after a 16-bit shift.
-__device__ __forceinline__ void drop_apply8(const DropCfg& d, uint64_t group, float (&v)[8]) {
-  const uint4 r = drop_bits8(d, group);
-  const uint32_t t = d.thresh << 16;
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = (w[i] << 16) >= t ? v[2 * i] * d.scale : 0.f;
-    v[2 * i + 1] = w[i] >= t ? v[2 * i + 1] * d.scale : 0.f;
-  }
-}
-
-// Per-thread dropout state for instruction-bound inner loops: the 7 Philox round keys live in registers
-// (seed + device counter folded in once), so a call is 14 IMAD.WIDE + 14 LOP3 for 8 decisions.
+// Per-thread part of a dropout stream: the device step counter, read once (2 registers).  Every call takes the
+// DropCfg it was built from -- pass the kernel parameter itself so that keys / site / threshold stay constant-bank
+// operands.
 struct DropState {
-  uint32_t ka[7], kb[7];
-  uint32_t site, thr;  // thr = thresh << 16 (0 => disabled)
+  uint32_t c1, c3;
   __device__ __forceinline__ explicit DropState(const DropCfg& d) {
-    const uint64_t seed = d.seed + (d.offset != nullptr ? 0x9E3779B97F4A7C15ull * __ldg(d.offset) : 0ull);
-    uint32_t a = static_cast<uint32_t>(seed), b = static_cast<uint32_t>(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 7; ++r) { ka[r] = a; kb[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
-    site = d.site;
-    thr = d.thresh << 16;
+    unsigned long long o = 0ull;
+    if (d.thresh != 0 && d.offset != nullptr) o = __ldg(d.offset);
+    c1 = static_cast<uint32_t>(o);
+    c3 = 0x9E3779B9u ^ static_cast<uint32_t>(o >> 32);
   }
-  // same stream as drop_bits8(cfg, group)
-  __device__ __forceinline__ uint4 bits(uint64_t group) const {
-    uint32_t c0 = static_cast<uint32_t>(group), c1 = static_cast<uint32_t>(group >> 32), c2 = site, c3 = 0x9E3779B9u;
+  // the 128 random bits of `group` (lane j of the group = 16-bit field j, low half first)
+  __device__ __forceinline__ uint4 bits(const DropCfg& d, uint64_t group) const {
+    uint32_t x0 = static_cast<uint32_t>(group), x1 = static_cast<uint32_t>(group >> 32) ^ c1, x2 = d.site, x3 = c3;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
-      const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
-      const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
-      const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ ka[r], n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ kb[r];
-      c1 = static_cast<uint32_t>(p1); c3 = static_cast<uint32_t>(p0);
-      c0 = n0; c2 = n2;
+      const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * x0;
+      const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * x2;
+      const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ x1 ^ d.ka[r], n2 = static_cast<uint32_t>(p0 >> 32) ^ x3 ^ d.kb[r];
+      x1 = static_cast<uint32_t>(p1); x3 = static_cast<uint32_t>(p0);
+      x0 = n0; x2 = n2;
     }
-    return make_uint4(c0, c1, c2, c3);
+    return make_uint4(x0, x1, x2, x3);
   }
-  // keep decision of element j (0..7) of the group whose bits are `r`
-  __device__ __forceinline__ bool keep(const uint4& r, int j) const {
-    const uint32_t w = j < 2 ? r.x : (j < 4 ? r.y : (j < 6 ? r.z : r.w));
-    return ((j & 1) ? w : (w << 16)) >= thr;
+  // v[j] = keep_j ? v[j] * scale : 0 for the 8 elements of `group`, without materialising the bit mask:
+  // the high field is compared in place (word >= thresh << 16), the low one after a 16-bit shift.
+  __device__ __forceinline__ void apply8(const DropCfg& d, uint64_t group, float (&v)[8]) const {
+    const uint4 r = bits(d, group);
+    const uint32_t t = d.thresh << 16;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = (w[i] << 16) >= t ? v[2 * i] * d.scale : 0.f;
+      v[2 * i + 1] = w[i] >= t ? v[2 * i + 1] * d.scale : 0.f;
+    }
+  }
+  // keep-mask bits (bit j = element j kept) of the 8 elements of `group`
+  __device__ __forceinline__ uint32_t keep8(const DropCfg& d, uint64_t group) const {
+    const uint4 r = bits(d, group);
+    const uint32_t t = d.thresh << 16;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      m |= ((w[i] << 16) >= t ? 1u : 0u) << (2 * i);
+      m |= (w[i] >= t ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
   }
 };
 

@@ -10,178 +10,245 @@ extern long long g_launches;
 
 constexpr int LN_WARPS = 8;
 
-// NCH = number of 8-element chunks per lane (cols <= NCH * 256)
-template <int NCH>
+constexpr int LNB_STAGES = 3;
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// (ld.volatile: ptxas otherwise merges the second pass's reads with the first pass's and keeps the whole row in
+//  registers -- exactly the pressure the shared-memory ring is there to remove)
+__device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
+constexpr int ln_fwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * nch * 512; }
+
+// NCH = number of 8-element chunks per lane (cols <= NCH * 256); EXACT: cols == NCH * 256, no chunk predicates
+// (the encoder's 768 and 512 columns) -- these kernels are as much issue-bound as HBM-bound, every instruction
+// per element counts.
+// Forward: rows arrive through a per-warp 3-deep cp.async ring (two rows in flight while one is normalised) -- with
+// plain loads a warp had one row (1.5 KB) outstanding for a third of its time and the kernel sat at 3.6 TB/s.
+template <int NCH, bool EXACT>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
-              int cols, float eps, DropCfg drop) {
+              int cols_rt, float eps, const DropCfg drop) {
   pdl_prologue();
+  extern __shared__ __align__(16) uint8_t lnf_ring[];
   const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int warp_global = blockIdx.x * LN_WARPS + warp;
   const int nwarps = gridDim.x * LN_WARPS;
-  const int nchunks = cols >> 3;
+  const int cols = EXACT ? NCH * 256 : cols_rt;
+  const int nchunks = EXACT ? NCH * 32 : cols_rt >> 3;
+  const float inv_cols = 1.0f / static_cast<float>(cols);
+  const DropState dstate(drop);
+  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(lnf_ring)) + warp * (LNB_STAGES * NCH * 512) + lane * 16;
+  auto issue = [&](int row, int stage) {
+    if (row < rows) {
+      const __nv_bfloat16* xr = x + static_cast<long long>(row) * cols + lane * 8;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+        if (EXACT || lane + 32 * i < nchunks) cp_async16(ring + (stage * NCH + i) * 512, xr + i * 256);
+    }
+    cp_async_commit();
+  };
+  issue(warp_global, 0);
+  issue(warp_global + nwarps, 1);
+  int stage = 0;
   for (int row = warp_global; row < rows; row += nwarps) {
-    const __nv_bfloat16* xr = x + static_cast<long long>(row) * cols;
+    issue(row + 2 * nwarps, stage + 2 >= LNB_STAGES ? stage + 2 - LNB_STAGES : stage + 2);
+    cp_async_wait<2>();
     float v[NCH][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
-        bf16x8_to_f32(ldg128(xr + c * 8), v[i]);
+      if (EXACT || lane + 32 * i < nchunks) {
+        bf16x8_to_f32(lds128(ring + (stage * NCH + i) * 512), v[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i][j];
       }
     }
-    const float mean = warp_sum(s) / cols;
+    const float mean = warp_sum(s) * inv_cols;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
+      if (EXACT || lane + 32 * i < nchunks) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = v[i][j] - mean;
-          sq += d * d;
+          sq = fmaf(d, d, sq);
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+    const float rstd = rsqrtf(warp_sum(sq) * inv_cols + eps);
     if (lane == 0) {
       mean_out[row] = mean;
       rstd_out[row] = rstd;
     }
-    __nv_bfloat16* yr = y + static_cast<long long>(row) * cols;
+    __nv_bfloat16* yr = y + static_cast<long long>(row) * cols + lane * 8;
+    const float nmr = -mean * rstd;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8 + 4));
+      if (EXACT || lane + 32 * i < nchunks) {
+        const int c8 = lane * 8 + i * 256;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[i][j], rstd, nmr), g[j], b[j]);
         if (drop.thresh != 0) {
-          drop_apply8(drop, static_cast<uint64_t>(row) * nchunks + c, o);
+          dstate.apply8(drop, static_cast<uint64_t>(row) * nchunks + lane + 32 * i, o);
         }
-        stg128(yr + c * 8, f32_to_bf16x8(o));
+        stg128(yr + i * 256, f32_to_bf16x8(o));
       }
     }
+    stage = stage + 1 == LNB_STAGES ? 0 : stage + 1;
   }
+  cp_async_wait<0>();
 }
 
 // Backward.  dy_eff = dy (* keep mask of the output dropout `din`, if the forward dropped the
 // LN output).  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).
 // Also emits dx_drop = dx * keep mask of `dout` (the dropout that sat on the GEMM output
 // feeding this LayerNorm's input) so the dgrad/wgrad GEMMs can consume it directly.
+//
+// The first version ran 42 instructions per element with the row and its prefetched successor in registers: it
+// was issue-bound (3.1 TB/s) and one step from spilling.  Now:
+//  * rows are staged through shared memory by 16-byte cp.async (LDGSTS, L2 -> smem, no registers): every warp owns a
+//    3-deep ring of (dy, x) rows, two rows are always in flight while one is reduced, and both passes read the row
+//    from its slot (lane-private 16-byte slots: no bank conflicts, no cross-lane synchronisation -- a lane only
+//    reads what it copied itself, cp.async.wait_group orders that);
+//  * pass 1 is xhat = fma(x, rstd, -mean rstd) plus four fused accumulations; pass 2 is
+//      dx = dy (rstd g) + x (-rstd^2 s2) + (-rstd (s1 - mean rstd s2))   -- one FMUL and two FMAs per element;
+//  * dropout round keys are constant-bank operands (DropState), EXACT drops the chunk predicates, the rare
+//    input-dropout path (one LayerNorm per step) is a template parameter.
 #ifndef LN_BWD_MINB
 #define LN_BWD_MINB 2
 #endif
 #ifndef LN_BWD_GRID_MULT
 #define LN_BWD_GRID_MULT 2
 #endif
-template <int NCH>
+constexpr int ln_bwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * 2 * nch * 512; }
+
+template <int NCH, bool EXACT, bool HAS_DIN>
 __global__ void __launch_bounds__(LN_WARPS * 32, LN_BWD_MINB)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, int rows, int cols, DropCfg din, DropCfg dout) {
+              float* __restrict__ dbeta, int rows, int cols_rt, const DropCfg din, const DropCfg dout) {
   pdl_prologue();
+  extern __shared__ __align__(16) uint8_t lnb_ring[];
   __shared__ float red[LN_WARPS][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warp_global = blockIdx.x * LN_WARPS + warp;
   const int nwarps = gridDim.x * LN_WARPS;
-  const int nchunks = cols >> 3;
+  const int cols = EXACT ? NCH * 256 : cols_rt;
+  const int nchunks = EXACT ? NCH * 32 : cols_rt >> 3;
+  const float inv_cols = 1.0f / static_cast<float>(cols);
+  const DropState st_in(din), st_out(dout);  // (st_in is dead code unless HAS_DIN)
+  // ring slot of (stage, dy|x, chunk i) for this lane: 512 bytes per (stage, tensor, chunk), 16 bytes per lane
+  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(lnb_ring)) + warp * (LNB_STAGES * 2 * NCH * 512) + lane * 16;
+  auto slot = [&](int stage, int which, int i) -> uint32_t { return ring + ((stage * 2 + which) * NCH + i) * 512; };
+  auto issue = [&](int row, int stage) {
+    if (row < rows) {
+      const long long off = static_cast<long long>(row) * cols + lane * 8;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        if (EXACT || lane + 32 * i < nchunks) {
+          cp_async16(slot(stage, 0, i), dy + off + i * 256);
+          cp_async16(slot(stage, 1, i), x + off + i * 256);
+        }
+      }
+    }
+    cp_async_commit();  // (an empty group past the end keeps the wait_group count uniform)
+  };
   float dg[NCH][8], db[NCH][8];
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
 
-  // The row is kept as the raw bf16 it was loaded as (and unpacked twice) instead of as fp32 products: that leaves
-  // the registers to have the NEXT row's loads in flight while this one is reduced and written -- the kernel is
-  // HBM-bound and a load -> shuffle-reduce -> store sequence per row left the memory pipe idle half of the time.
-  uint4 nd[NCH], nx[NCH];
+  issue(warp_global, 0);
+  issue(warp_global + nwarps, 1);
   float nmean = 0.f, nrstd = 0.f;
-  auto fetch = [&](int row) {
-    const long long off = static_cast<long long>(row) * cols;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
-        nd[i] = ldg128(dy + off + c * 8);
-        nx[i] = ldg128(x + off + c * 8);
-      }
-    }
-    nmean = __ldg(mean_in + row);
-    nrstd = __ldg(rstd_in + row);
-  };
-  if (warp_global < rows) fetch(warp_global);
+  if (warp_global < rows) {
+    nmean = __ldg(mean_in + warp_global);
+    nrstd = __ldg(rstd_in + warp_global);
+  }
+  int stage = 0;
   for (int row = warp_global; row < rows; row += nwarps) {
-    const long long off = static_cast<long long>(row) * cols;
-    uint4 rd[NCH], rx[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) { rd[i] = nd[i]; rx[i] = nx[i]; }
-    const float mean = nmean, rstd = nrstd;
-    if (row + nwarps < rows) fetch(row + nwarps);
+    {  // refill the slot that was consumed in the previous trip (this thread's reads of it have retired)
+      const int s2 = stage + 2 >= LNB_STAGES ? stage + 2 - LNB_STAGES : stage + 2;
+      issue(row + 2 * nwarps, s2);
+    }
+    const float rstd = nrstd, nmr = -nmean * nrstd;
+    if (row + nwarps < rows) {
+      nmean = __ldg(mean_in + row + nwarps);
+      nrstd = __ldg(rstd_in + row + nwarps);
+    }
+    cp_async_wait<2>();  // everything but the two youngest groups has landed: this row is in its slot
+    const long long off = static_cast<long long>(row) * cols + lane * 8;
+    const uint64_t grp0 = static_cast<uint64_t>(row) * nchunks + lane;  // dropout group of chunk i: grp0 + 32 i
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
+      if (EXACT || lane + 32 * i < nchunks) {
         float d[8], xv[8];
-        bf16x8_to_f32(rd[i], d);
-        bf16x8_to_f32(rx[i], xv);
-        if (din.thresh != 0) {
-          drop_apply8(din, static_cast<uint64_t>(row) * nchunks + c, d);
-        }
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+        bf16x8_to_f32(lds128(slot(stage, 0, i)), d);
+        bf16x8_to_f32(lds128(slot(stage, 1, i)), xv);
+        if (HAS_DIN) st_in.apply8(din, grp0 + 32 * i, d);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          const float gy = d[j] * g[j];
-          s1 += gy;
-          s2 += gy * xh;
-          dg[i][j] += d[j] * xh;
+          const float xh = fmaf(xv[j], rstd, nmr);
+          const float t = d[j] * xh;
+          s1 = fmaf(d[j], g[j], s1);
+          s2 = fmaf(t, g[j], s2);
+          dg[i][j] += t;
           db[i][j] += d[j];
         }
       }
     }
-    s1 = warp_sum(s1) / cols;
-    s2 = warp_sum(s2) / cols;
+    s1 = warp_sum(s1) * inv_cols;
+    s2 = warp_sum(s2) * inv_cols;
+    // dx = rstd (d g - s1 - xh s2),  xh = x rstd + nmr
+    const float cb = -rstd * rstd * s2;
+    const float cc = -rstd * fmaf(nmr, s2, s1);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
+      if (EXACT || lane + 32 * i < nchunks) {
         float d[8], xv[8], o[8];
-        bf16x8_to_f32(rd[i], d);
-        bf16x8_to_f32(rx[i], xv);
-        if (din.thresh != 0) {
-          drop_apply8(din, static_cast<uint64_t>(row) * nchunks + c, d);  // (regenerated: one LN instance per step)
-        }
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+        bf16x8_to_f32(lds128(slot(stage, 0, i)), d);
+        bf16x8_to_f32(lds128(slot(stage, 1, i)), xv);
+        if (HAS_DIN) st_in.apply8(din, grp0 + 32 * i, d);  // (regenerated: one LN instance per step)
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * g[j] - s1 - ((xv[j] - mean) * rstd) * s2);
-        stg128(dx + off + c * 8, f32_to_bf16x8(o));
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(d[j], rstd * g[j], fmaf(xv[j], cb, cc));
+        stg128(dx + off + i * 256, f32_to_bf16x8(o));
         if (dx_drop != nullptr) {
           if (dout.thresh != 0) {
-            drop_apply8(dout, static_cast<uint64_t>(row) * nchunks + c, o);
+            st_out.apply8(dout, grp0 + 32 * i, o);
           }
-          stg128(dx_drop + off + c * 8, f32_to_bf16x8(o));
+          stg128(dx_drop + off + i * 256, f32_to_bf16x8(o));
         }
       }
     }
+    stage = stage + 1 == LNB_STAGES ? 0 : stage + 1;
   }
+  cp_async_wait<0>();
   // block reduction of the per-warp partial dgamma / dbeta, then one atomic per column
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -248,14 +315,109 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restri
   }
 }
 
+template <int NCH, bool EXACT, typename... Args>
+static int launch_ln_fwd(int grid, cudaStream_t st, Args... args) {
+  auto kfn = ln_fwd_kernel<NCH, EXACT>;
+  static bool configured = false;
+  if (!configured) {
+    MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_fwd_smem_bytes(NCH)));
+    configured = true;
+  }
+  MH_CUDA(launch_pdl(kfn, dim3(grid), dim3(LN_WARPS * 32), ln_fwd_smem_bytes(NCH), st, args...));
+  return 0;
+}
+
+template <int NCH, bool EXACT, bool HAS_DIN, typename... Args>
+static int launch_ln_bwd(int grid, cudaStream_t st, Args... args) {
+  auto kfn = ln_bwd_kernel<NCH, EXACT, HAS_DIN>;
+  static bool configured = false;  // the row ring needs the > 48 KB opt-in
+  if (!configured) {
+    MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_bwd_smem_bytes(NCH)));
+    configured = true;
+  }
+  MH_CUDA(launch_pdl(kfn, dim3(grid), dim3(LN_WARPS * 32), ln_bwd_smem_bytes(NCH), st, args...));
+  return 0;
+}
+
+// Narrow matrices (cols <= 1024: the [B*T, 768] gradients behind the out_proj / fc2 bias gradients): the slab kernel
+// above has 3 column slabs x ~200 row slices of ~120 rows -- too little work per block, 2.6 TB/s.  Here a warp owns
+// whole rows (NCH 16-byte chunks per lane) and keeps FOUR rows in flight per trip; per-lane column sums stay in
+// registers and leave through the same block reduction + one atomic per column.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int rows, int cols) {
+  pdl_prologue();
+  __shared__ float red[8][32 * 8 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * 8;
+  const int nchunks = cols >> 3;
+  float acc[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  int row = blockIdx.x * 8 + warp;
+  for (; row + 3 * nwarps < rows; row += 4 * nwarps) {
+    uint4 q[4][NCH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+        if (lane + 32 * i < nchunks) q[u][i] = ldg128(x + static_cast<long long>(row + u * nwarps) * ld + lane * 8 + i * 256);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+        if (lane + 32 * i < nchunks) {
+          float v[8];
+          bf16x8_to_f32(q[u][i], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += v[j];
+        }
+  }
+  for (; row < rows; row += nwarps) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+      if (lane + 32 * i < nchunks) {
+        float v[8];
+        bf16x8_to_f32(ldg128(x + static_cast<long long>(row) * ld + lane * 8 + i * 256), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += v[j];
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[i][j];
+    __syncthreads();
+    const int col = i * 256 + threadIdx.x;
+    if (col < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      atomicAdd(out + col, t);
+    }
+  }
+}
+
 template <typename F>
 static int dispatch_nch(int cols, F&& f) {
   const int nch = (cols / 8 + 31) / 32;
+  if (cols == nch * 256) {  // whole chunks only: predicate-free kernels
+    switch (nch) {
+      case 1: return f(std::integral_constant<int, 1>(), std::true_type());
+      case 2: return f(std::integral_constant<int, 2>(), std::true_type());
+      case 3: return f(std::integral_constant<int, 3>(), std::true_type());
+      case 4: return f(std::integral_constant<int, 4>(), std::true_type());
+      default: break;
+    }
+  }
   switch (nch) {
-    case 1: return f(std::integral_constant<int, 1>());
-    case 2: return f(std::integral_constant<int, 2>());
-    case 3: return f(std::integral_constant<int, 3>());
-    case 4: return f(std::integral_constant<int, 4>());
+    case 1: return f(std::integral_constant<int, 1>(), std::false_type());
+    case 2: return f(std::integral_constant<int, 2>(), std::false_type());
+    case 3: return f(std::integral_constant<int, 3>(), std::false_type());
+    case 4: return f(std::integral_constant<int, 4>(), std::false_type());
     default: set_error("LayerNorm supports up to 1024 columns (got %d)", cols); return 1;
   }
 }
@@ -268,12 +430,15 @@ extern "C" int mh_layernorm_fwd(const void* x, const float* gamma, const float* 
                                 uint32_t site, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm: bad shape %d x %d", rows, cols);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * 8);
+  // resident blocks only (4 per SM at 64 registers / 37 KB of ring): a warp then walks >= 5 rows at the bench shape
+  // and its ring stays primed
+  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * 4);
   const DropCfg d = make_drop(p_drop, seed, site);
-  return dispatch_nch(cols, [&](auto nch) {
-    MH_CUDA(launch_pdl(ln_fwd_kernel<decltype(nch)::value>, dim3(grid), dim3(LN_WARPS * 32), 0, st,
-                       reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd,
-                       rows, cols, eps, d));
+  return dispatch_nch(cols, [&](auto nch, auto exact) {
+    const int rc = launch_ln_fwd<decltype(nch)::value, decltype(exact)::value>(
+        grid, st, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, rows, cols,
+        eps, d);
+    if (rc != 0) return rc;
     ++g_launches;
     return 0;
   });
@@ -287,11 +452,13 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_BWD_GRID_MULT);
   const DropCfg din = make_drop(p_in, seed_in, site_in), dout = make_drop(p_out, seed_out, site_out);
-  return dispatch_nch(cols, [&](auto nch) {
-    MH_CUDA(launch_pdl(ln_bwd_kernel<decltype(nch)::value>, dim3(grid), dim3(LN_WARPS * 32), 0, st,
-                       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
-                       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows,
-                       cols, din, dout));
+  return dispatch_nch(cols, [&](auto nch, auto exact) {
+    constexpr int N = decltype(nch)::value;
+    constexpr bool E = decltype(exact)::value;
+    const int rc = din.thresh != 0
+                       ? launch_ln_bwd<N, E, true>(grid, st, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows, cols, din, dout)
+                       : launch_ln_bwd<N, E, false>(grid, st, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows, cols, din, dout);
+    if (rc != 0) return rc;
     ++g_launches;
     return 0;
   });
@@ -300,6 +467,18 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
 extern "C" int mh_colsum(const void* x, long long ld, float* out, int rows, int cols, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, "colsum: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cols <= 1024 && rows >= 4096) {
+    const int grid = sm_count() * 2;
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    switch ((cols + 255) / 256) {
+      case 1: MH_CUDA(launch_pdl(colsum_rows_kernel<1>, dim3(grid), dim3(256), 0, st, xp, ld, out, rows, cols)); break;
+      case 2: MH_CUDA(launch_pdl(colsum_rows_kernel<2>, dim3(grid), dim3(256), 0, st, xp, ld, out, rows, cols)); break;
+      case 3: MH_CUDA(launch_pdl(colsum_rows_kernel<3>, dim3(grid), dim3(256), 0, st, xp, ld, out, rows, cols)); break;
+      default: MH_CUDA(launch_pdl(colsum_rows_kernel<4>, dim3(grid), dim3(256), 0, st, xp, ld, out, rows, cols)); break;
+    }
+    ++g_launches;
+    return 0;
+  }
   const int gx = (cols + 255) / 256;
   int gy = (sm_count() * 4 + gx - 1) / gx;
   int rpb = (rows + gy - 1) / gy;

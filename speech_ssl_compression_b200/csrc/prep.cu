@@ -192,12 +192,13 @@ __global__ void gather_labels_kernel(const long long* __restrict__ label, const 
 
 // y = x * keep(seed, site) / (1 - p), element index = row * cols + col (the GEMM-epilogue indexing)
 __global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long groups,
-                                     DropCfg drop) {
+                                     const DropCfg drop) {
+  const DropState dstate(drop);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v[8];
     bf16x8_to_f32(ldg128(x + i * 8), v);
-    drop_apply8(drop, static_cast<uint64_t>(i), v);
+    dstate.apply8(drop, static_cast<uint64_t>(i), v);
     stg128(y + i * 8, f32_to_bf16x8(v));
   }
 }

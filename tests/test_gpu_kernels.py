@@ -297,7 +297,7 @@ def test_attention_full_size_properties():
 
 
 # ------------------------------------------------------------------------------------- layer norm
-@pytest.mark.parametrize("rows,cols", [(3000, 768), (257, 768), (64, 512)])
+@pytest.mark.parametrize("rows,cols", [(3000, 768), (257, 768), (64, 512), (24000, 768), (5000, 80), (9001, 1000), (1, 768)])
 def test_layernorm_fwd_bwd(rows, cols):
     k = K()
     x = (torch.randn(rows, cols, device=DEV) * 2 + 0.5).to(bf16)
@@ -348,6 +348,13 @@ def test_colsum_and_casts():
     out = torch.ones(768, device=DEV)
     k.colsum_add(x[:, 768:1536], out)
     assert rel(out, 1 + x[:, 768:1536].float().sum(0)) < 1e-4
+    # narrow + tall matrices take the row-per-warp kernel (4 rows in flight, ragged tail, strided view, odd widths)
+    for rows, cols, ld in [(24000, 768, 768), (4099, 768, 2304), (9001, 1000, 1000), (5000, 80, 80)]:
+        big = torch.randn(rows, ld, device=DEV).to(bf16)
+        view = big[:, ld - cols:] if ld != cols else big
+        acc = torch.full((cols,), 2.0, device=DEV)
+        k.colsum_add(view, acc)
+        assert rel(acc, 2 + view.float().sum(0)) < 1e-4, (rows, cols, ld)
     f = torch.randn(1000, 80, device=DEV)
     assert torch.equal(k.to_bf16(f), f.to(bf16))
     assert torch.equal(k.to_f32(f.to(bf16)), f.to(bf16).float())

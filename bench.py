@@ -90,7 +90,7 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, power = [], None, set(), []
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
@@ -100,13 +100,19 @@ class ClockSampler:
                 smax = float(parts[1])
             except ValueError:
                 continue
+            try:
+                power.append(float(parts[2]))
+            except ValueError:
+                pass
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         busy = [x for x in sm if smax and x > 0.5 * smax] or sm
         med = busy[len(busy) // 2] if busy else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        power.sort()
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": power[-1] if power else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -345,12 +351,17 @@ def main():
     barrier()
     n0 = K.L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
     e0.record()
     for _ in range(args.steps):
         ts.run()
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()  # (a time stamp between two graph launches: no synchronisation, no extra work)
+        marks.append(m)
     e1.record()
     barrier()
     ms_resident = e0.elapsed_time(e1) / args.steps
+    series = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     eager_launches = K.L.launch_count() - n0
 
     # ---- (2) end to end through the public step API: H2D of the batch (pinned) + step + D2H of the loss
@@ -409,6 +420,7 @@ def main():
         "gpu_launches": int(ts.launches_per_step * args.steps if ts.use_graph else eager_launches),
         "launches_per_step": int(ts.launches_per_step),
         "clocks": clocks,
+        "ms_per_step_series": [round(x, 3) for x in series],  # rank 0; a rising series = the power cap pulling clocks down
         "roofline": roof,
         "step_mfu": {"algorithmic_tflops": step_flops / (ms_resident / 1e3) / 1e12 / world,
                      "peak_sustained_tflops": sustained,

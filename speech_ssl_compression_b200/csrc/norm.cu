@@ -429,6 +429,11 @@ extern "C" int mh_layernorm_fwd(const void* x, const float* gamma, const float* 
                                 float* rstd, int rows, int cols, float eps, float p_drop, uint64_t seed,
                                 uint32_t site, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm: bad shape %d x %d", rows, cols);
+  MH_CHECK(x != nullptr && y != nullptr && gamma != nullptr && beta != nullptr && mean != nullptr && rstd != nullptr,
+           "layernorm: null pointer");
+  MH_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+             reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+           "layernorm: x, y, gamma and beta must be 16-byte aligned (rows are moved as 16-byte chunks)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // resident blocks only (4 per SM at 64 registers / 37 KB of ring): a warp then walks >= 5 rows at the bench shape
   // and its ring stays primed
@@ -449,6 +454,12 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
                                 int cols, float p_in, uint64_t seed_in, uint32_t site_in, float p_out,
                                 uint64_t seed_out, uint32_t site_out, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm_bwd: bad shape %d x %d", rows, cols);
+  MH_CHECK(dy != nullptr && x != nullptr && gamma != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr &&
+               dgamma != nullptr && dbeta != nullptr,
+           "layernorm_bwd: null pointer");
+  MH_CHECK(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) |
+             reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop)) & 15) == 0,
+           "layernorm_bwd: dy, x, gamma, dx and dx_drop must be 16-byte aligned (rows are moved as 16-byte chunks)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_BWD_GRID_MULT);
   const DropCfg din = make_drop(p_in, seed_in, site_in), dout = make_drop(p_out, seed_out, site_out);
@@ -465,7 +476,9 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
 }
 
 extern "C" int mh_colsum(const void* x, long long ld, float* out, int rows, int cols, void* stream) {
-  MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, "colsum: bad shape");
+  MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols, "colsum: bad shape %d x %d (ld %lld)", rows, cols, ld);
+  MH_CHECK(x != nullptr && out != nullptr && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+           "colsum: x must be a 16-byte aligned bf16 matrix");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cols <= 1024 && rows >= 4096) {
     const int grid = sm_count() * 2;

@@ -44,6 +44,33 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.mh_last_error(), bytes)
 
 
+def test_argument_validation_fails_loudly_before_any_device_work():
+    """Shape / alignment violations are errors with a message (never a fallback, never a device fault): the checks
+    sit in front of the first CUDA call, so they can be exercised without a GPU."""
+    lib = ctypes.CDLL(os.path.join(PKG, "libmh_b200.so"))
+    lib.mh_last_error.restype = ctypes.c_char_p
+    vp, fp = ctypes.c_void_p, ctypes.c_void_p
+    buf = ctypes.create_string_buffer(4096)
+    base = (ctypes.addressof(buf) + 63) & ~63          # 64-byte aligned host address (never dereferenced)
+    lib.mh_layernorm_fwd.argtypes = [vp, fp, fp, vp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_uint64, ctypes.c_uint32, vp]
+    lib.mh_colsum.argtypes = [vp, ctypes.c_longlong, fp, ctypes.c_int, ctypes.c_int, vp]
+    # columns not a multiple of 8
+    assert lib.mh_layernorm_fwd(base, base, base, base, base, base, 4, 60, 1e-5, 0.0, 0, 0, None) != 0
+    assert b"bad shape" in lib.mh_last_error()
+    # misaligned row pointer
+    assert lib.mh_layernorm_fwd(base + 2, base, base, base, base, base, 4, 64, 1e-5, 0.0, 0, 0, None) != 0
+    assert b"16-byte aligned" in lib.mh_last_error()
+    # null output
+    assert lib.mh_layernorm_fwd(base, base, base, None, base, base, 4, 64, 1e-5, 0.0, 0, 0, None) != 0
+    assert b"null" in lib.mh_last_error()
+    # column sums: leading dimension smaller than the width, misaligned base
+    assert lib.mh_colsum(base, 8, base, 4, 64, None) != 0
+    assert b"bad shape" in lib.mh_last_error()
+    assert lib.mh_colsum(base + 2, 64, base, 4, 64, None) != 0
+    assert b"aligned" in lib.mh_last_error()
+
+
 def test_header_cites_the_reference_for_every_kernel_family():
     text = open(os.path.join(ROOT, "include", "mh_b200.h")).read()
     for cite in ("forward_multihead_attention.py", "module.py", "model.py", "pretrain_expert.py", "prune.py", "runner.py"):

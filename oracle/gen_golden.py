@@ -141,6 +141,39 @@ def sec_forward20():
     save("forward20", **arrs)
 
 
+LENS10 = [1500, 1311]
+
+
+def sec_forward10():
+    """cfg3's shape: base 12L 10 ms (D_in = 40, 1500 frames, mask spans of 10): eval forward + masked train
+    forward / backward (dropout 0) on two utterances."""
+    cfg = base_cfg(10, 12)
+    sd = O.synth_state_dict(cfg, seed=13)
+    m = ref_model(cfg, sd)
+    feat, label, pad = O.synth_batch(2, 1500, 40, LENS10, seed=21)
+    m.eval()
+    with torch.no_grad():
+        out = m(feat.clone(), pad, get_hidden=True, no_pred=True)
+    arrs = {"eval_hidden": sub(out[0], 50, 32), "eval_pre_feat": sub(out[6], 50, 32)}
+    arrs["eval_layers"] = np.stack([sub(h, 50, 32) for h in out[5]])
+    arrs["eval_absmean"] = np.array([float(h.abs().mean()) for h in out[5]])
+    m.train()
+    np.random.seed(1337)
+    hidden, logit_m, _, label_m, _, _, _, mask_idx = m(feat.clone(), pad, label, mask=True)
+    loss = torch.nn.CrossEntropyLoss(ignore_index=-100, reduction="mean")(logit_m, label_m)
+    loss.backward()
+    arrs["train_mask"] = np.packbits(mask_idx.numpy())
+    arrs["train_label_m"] = label_m.numpy()
+    arrs["train_logit_m"] = logit_m.detach()[::11, ::16].numpy()
+    arrs["train_loss"] = np.array([float(loss)])
+    gn = {n: float(p.grad.norm()) for n, p in m.named_parameters()}
+    keys = sorted(gn)
+    arrs["grad_names"] = np.array(keys)
+    arrs["grad_norms"] = np.array([gn[k] for k in keys])
+    print("loss", float(loss), "N_m", label_m.numel())
+    save("forward10", **arrs)
+
+
 class _Holder:
     """Stands in for the expert object the tools poke (needs .model / .upstream_config)."""
 
@@ -344,6 +377,7 @@ SECTIONS = {
     "span_mask": sec_span_mask,
     "init": sec_init,
     "forward20": sec_forward20,
+    "forward10": sec_forward10,
     "head_prune": sec_head_prune,
     "row_prune": sec_row_prune,
     "weight_prune": sec_weight_prune,

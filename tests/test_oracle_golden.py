@@ -89,6 +89,35 @@ def test_train_forward_backward_matches_reference(golden, fwd20):
     np.testing.assert_allclose(sdg["encoder.pos_conv.0.weight_g"].grad.numpy(), g["grad_pos_g"], atol=1e-6, rtol=2e-3)
 
 
+def test_10ms_forward_backward_matches_reference(golden):
+    """cfg3's shape (10 ms frames: D_in = 40, 1500 frames, mask spans of 10) against the reference's own run."""
+    lens = [1500, 1311]
+    cfg = base_cfg(10, 12)
+    sd = O.synth_state_dict(cfg, seed=13)
+    feat, label, pad = O.synth_batch(2, 1500, 40, lens, seed=21)
+    g = golden("forward10")
+    with torch.no_grad():
+        out = O.model_forward(sd, cfg, feat, pad, no_pred=True)
+    np.testing.assert_allclose(sub(out["hidden"], 50, 32), g["eval_hidden"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(sub(out["pre_feat"], 50, 32), g["eval_pre_feat"], atol=1e-5, rtol=1e-5)
+    for i, h in enumerate(out["layer_hiddens"]):
+        np.testing.assert_allclose(sub(h, 50, 32), g["eval_layers"][i], atol=2e-4, rtol=1e-4)
+        assert abs(float(h.abs().mean()) - g["eval_absmean"][i]) < 1e-4
+    np.random.seed(1337)
+    mask = torch.from_numpy(O.span_mask(2, 1500, lens, 0.7, 10))
+    assert np.array_equal(np.packbits(mask.numpy()), g["train_mask"])                     # bit-exact span mask
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.model_forward(sdg, cfg, feat, pad, label, mask_indices=mask)
+    assert np.array_equal(out["label_m"].numpy(), g["train_label_m"])                     # bit-exact label gather
+    np.testing.assert_allclose(out["logit_m"].detach()[::11, ::16].numpy(), g["train_logit_m"], atol=3e-4, rtol=1e-4)
+    loss = O.ce_mean(out["logit_m"], out["label_m"])
+    assert abs(float(loss) - g["train_loss"][0]) < 2e-5
+    loss.backward()
+    for n, ref in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        got = float(sdg[n].grad.norm())
+        assert abs(got - ref) <= 2e-4 * max(ref, 1e-3) + 1e-7, (n, got, ref)
+
+
 def test_head_scores_and_selection(golden):
     g = golden("head_prune")
     cfg = base_cfg(10, 12)

@@ -126,6 +126,46 @@ def test_train_step_matches_reference_golden(golden, fwd20):
     assert rel_sub(params["encoder.pos_conv.0.weight_g"].grad.cpu().numpy(), g["grad_pos_g"]) < 5e-2
 
 
+# ------------------------------------------------------------------- cfg3's shape: 10 ms frames
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: first hardware run pending "
+                                        "(the CPU oracle is pinned against the same golden in tests/test_oracle_golden.py)")
+def test_10ms_eval_and_train_step_match_reference_golden(golden):
+    """D_in = 40, 1500 frames, mask spans of 10 (12 attention key blocks per row, K = 40 pre-projection GEMM)."""
+    from speech_ssl_compression_b200 import ops
+
+    lens = [1500, 1311]
+    cfg = base_cfg(10, 12)
+    sd = O.synth_state_dict(cfg, seed=13)
+    feat, label, pad = O.synth_batch(2, 1500, 40, lens, seed=21)
+    g = golden("forward10")
+    m = build(cfg, sd).eval()
+    with torch.no_grad():
+        out = m(feat.to(DEV), pad.to(DEV), get_hidden=True, no_pred=True)
+    assert rel_sub(sub(out[6], 50, 32), g["eval_pre_feat"]) < 6e-3
+    for i, h in enumerate(out[5]):
+        assert rel_sub(sub(h, 50, 32), g["eval_layers"][i]) < 2e-2, i
+    assert rel_sub(sub(out[0], 50, 32), g["eval_hidden"]) < 2e-2
+    m.train()
+    np.random.seed(1337)
+    out = m(feat.to(DEV), pad.to(DEV), label.to(DEV), mask=True, valid_lens=lens)
+    logit_m, label_m, mask_idx = out[1], out[3], out[7]
+    assert np.array_equal(np.packbits(mask_idx.cpu().numpy()), g["train_mask"])       # bit-exact span mask
+    assert np.array_equal(label_m.cpu().numpy(), g["train_label_m"])                  # bit-exact label gather
+    assert rel_sub(logit_m.detach().float().cpu()[::11, ::16].numpy(), g["train_logit_m"]) < 2.5e-2
+    loss = ops.cross_entropy(logit_m, label_m)
+    assert abs(float(loss.detach()) - g["train_loss"][0]) < 2e-2
+    loss.backward()
+    params = dict(m.named_parameters())
+    bad = []
+    for n, ref in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        if ".k_proj.bias" in n:
+            continue  # analytically zero gradient
+        got = float(params[n].grad.norm())
+        if abs(got - ref) > 5e-2 * max(ref, 1e-6):
+            bad.append((n, got, ref))
+    assert not bad, bad[:5]
+
+
 def test_masking_in_place_and_unmasked_predictions():
     """model.py:80 masks the caller's tensor in place; skip_nomask=False adds the unmasked set."""
     cfg = base_cfg(20, 2, skip_nomask=False)

@@ -172,7 +172,8 @@ def run_reference_arm(args):
     out = {"impl": "reference", "metric": "train frames/s", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args, per_gpu_batch=B),
+           "config": dict(workload_config(args, per_gpu_batch=B), cuda_graph=False,
+                          l2="CPU run: the working set streams through the host caches"),
            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}

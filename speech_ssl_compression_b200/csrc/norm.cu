@@ -1,6 +1,7 @@
-// LayerNorm forward / backward and bias-gradient column sums.  HBM-bound kernels: one warp
-// per row, 16-byte loads, fp32 statistics, warp-shuffle reductions, no shared-memory staging
-// of the row (each element is touched once).
+// LayerNorm forward / backward and bias-gradient column sums: one warp per row, fp32 statistics,
+// warp-shuffle reductions.  Rows reach a warp through its private 3-deep cp.async ring in shared
+// memory (16-byte chunks, lane-private slots): two rows are in flight while one is reduced and
+// no registers are spent on prefetch.
 #include "mh_b200.h"
 #define MH_PDL_FAMILY 4
 #include "mh_common.cuh"
@@ -29,8 +30,10 @@ constexpr int ln_fwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * nch * 
 // NCH = number of 8-element chunks per lane (cols <= NCH * 256); EXACT: cols == NCH * 256, no chunk predicates
 // (the encoder's 768 and 512 columns) -- these kernels are as much issue-bound as HBM-bound, every instruction
 // per element counts.
-// Forward: rows arrive through a per-warp 3-deep cp.async ring (two rows in flight while one is normalised) -- with
-// plain loads a warp had one row (1.5 KB) outstanding for a third of its time and the kernel sat at 3.6 TB/s.
+// Forward: same ring as the backward.  MEASURED: neutral here (17.9 us per launch inside the step either way).  ncu
+// (profiles/r01_q_ncu_ln_fwd.txt): the output stays in L2, DRAM sees 2 TB/s, issue slots are 33 % busy and 46 % of
+// the stalls are long-scoreboard -- the kernel is bound by the latency chain of one row per warp (load -> two
+// dependent shuffle reductions -> store), not by bandwidth; interleaving two rows per warp is the open lever.
 template <int NCH, bool EXACT>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,

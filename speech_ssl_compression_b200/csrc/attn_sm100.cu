@@ -21,6 +21,11 @@
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
 
+// MH_ATTN_V1 (build variant, A/B only): the first forward kernel and its keep-bit layout
+#ifndef MH_ATTN_V1
+#define MH_ATTN_V1 0
+#endif
+
 namespace mh {
 extern long long g_launches;
 int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
@@ -352,6 +357,426 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
   if (warp == 5) tmem_dealloc(tmem_base, FWD_TMEM_COLS);
 }
 
+// ----------------------------------------------------------------------------- forward, version 2
+// One CTA per (batch, head, 128-query tile), TWO CTAs per SM.  What changed against version 1 and why (ncu of v1:
+// tensor pipe 14 % active, issue slots 57 % busy, the four softmax warps of a CTA stalled together behind the
+// S -> softmax -> P -> PV -> S hand-off, 13-14 executed instructions per score):
+//   * S is DOUBLE-BUFFERED in TMEM (2 x 64 columns): S_{j+1} = Q K_{j+1}^T is complete long before the softmax of
+//     block j ends, so the softmax warps never wait for the tensor pipe (S_{j+2} is issued right behind P_j V_j).
+//   * P never touches shared memory: the bf16 probabilities are written back into the TMEM columns of their own
+//     score block (tcgen05.st) and P_j V_j takes its A operand from TMEM -- no st.shared, no fence.proxy.async.
+//   * packed fp32 arithmetic (FFMA2 / FADD2: two scores per instruction) for the exponent argument and the row sum.
+//   * no running-maximum pass after the first block: later blocks exponentiate against the reference of block 0 and
+//     only check that their row sum stayed far from overflow (any reference gives the exact softmax; fp32 sums and
+//     bf16 probabilities share the fp32 exponent range); the reference is raised on a rare, out-of-line path.
+//   * bit-sliced dropout: three Philox4x32-7 calls give twelve 32-bit planes, a 12-step LOP3 chain compares the
+//     twelve-bit random number of each of 32 keys with the threshold (1 instruction per plane for 32 decisions),
+//     the result IS the keep word saved for the backward; byte-MSB replication (PRMT) expands it to the 16-bit
+//     masks of the packed bf16 pairs.  p is quantised to 1/4096 (0.1 -> 410/4096 = 0.100098, scale 4096/3686).
+// Per score with dropout: ~7 executed instructions (13-14 in v1), ~2.7 without (7.2).
+// Key-block size BKV = 32: S[2] (2 x 32 columns) + O (64) = 128 TMEM columns and 48 KB of shared memory per CTA, so
+// FOUR CTAs share an SM (16 softmax warps, 4 per scheduler; <= 85 registers per thread).  Measured with BKV = 64
+// (2 CTAs per SM, 2 softmax warps per scheduler): 159 us, issue slots 46 % busy, 25 % of the stall samples "wait"
+// (fixed-latency dependencies) -- two warps per scheduler do not cover each other's dependency stalls.
+#ifndef MH_F2_BKV
+#define MH_F2_BKV 32
+#endif
+#ifndef MH_F2_KO
+#define MH_F2_KO 0  // knock-out experiments (timing only, wrong results): 1 no MUFU, 2 no Philox, 4 no keep store, 8 no TMEM load
+#endif
+template <int BKV>
+struct F2Cfg {
+  static constexpr int kStages = BKV == 32 ? 4 : 3;          // K ring and V ring depth
+  static constexpr int kTile = BKV * 128;                    // one K or V block: BKV keys x 128 B
+  static constexpr int kSmem = TILE_BYTES + 2 * kStages * kTile + 256;
+  static constexpr int kTmemCols = BKV == 32 ? 128 : 256;    // S[2] + O(64) -> next power of two
+#ifdef MH_F2_CTAS
+  static constexpr int kCtasPerSm = MH_F2_CTAS;
+#else
+  static constexpr int kCtasPerSm = BKV == 32 ? 4 : 2;
+#endif
+  static constexpr int kOCol = 2 * BKV;                      // first TMEM column of O
+};
+
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt_sel(uint32_t a) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(m) : "r"(a), "n"(SEL));
+  return m;
+}
+
+// Keep word of a 32-key chunk (version 2 layout): key e = 2 t + h (pair t = 2 s + u of the packed bf16 pairs, half h)
+// sits at bit 15 + 16 h - s - 8 u, so that the 16-bit masks of pair t are the replicated most significant bits of
+// bytes (1, 3) [u = 0] or (0, 2) [u = 1] of (word << s): 7 shifts + 16 PRMT for 32 keys.
+__host__ __device__ constexpr int keep_bit_pos2(int e) { return 15 + 16 * (e & 1) - (e >> 2) - 8 * ((e >> 1) & 1); }
+// masks of the 16 pairs of a chunk from its keep word
+__device__ __forceinline__ void keep_pair_masks(uint32_t kw, uint32_t (&m)[16]) {
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const uint32_t a = kw << s;
+    m[2 * s] = prmt_sel<0xBB99>(a);
+    m[2 * s + 1] = prmt_sel<0xAA88>(a);
+  }
+}
+
+struct AttnDrop2 {
+  uint32_t tmask[12];  // plane k: all-ones when bit k of the 12-bit threshold is set
+  float keep_scale;    // 4096 / (4096 - thr12)
+  float lg_scale;      // log2(keep_scale)
+};
+__host__ inline AttnDrop2 make_drop2(float p) {
+  AttnDrop2 d;
+  uint32_t thr = p > 0.f ? static_cast<uint32_t>(p * 4096.0f + 0.5f) : 0u;
+  if (thr > 4095u) thr = 4095u;
+  for (int k = 0; k < 12; ++k) d.tmask[k] = ((thr >> k) & 1u) ? 0xffffffffu : 0u;
+  d.keep_scale = 4096.0f / static_cast<float>(4096u - thr);
+  d.lg_scale = log2f(d.keep_scale);
+  return d;
+}
+
+#ifndef MH_F2_TRACE
+#define MH_F2_TRACE 0  // debug build: clock64 stamps of one CTA per SM-slot sample (mh_attn_trace_read)
+#endif
+#if MH_F2_TRACE
+__device__ long long g_f2_trace[8][64][8];
+#define F2_STAMP(slot, blk, what) do { if (trace_cta >= 0 && (blk) < 64) g_f2_trace[trace_cta][blk][what] = clock64(); } while (0)
+#else
+#define F2_STAMP(slot, blk, what) do { } while (0)
+#endif
+
+template <int BKV>
+__global__ void __launch_bounds__(192, F2Cfg<BKV>::kCtasPerSm)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tm_out, const AttnParams p, const AttnDrop2 d2) {
+  using Cfg = F2Cfg<BKV>;
+  constexpr int NST = Cfg::kStages, KV_TILE = Cfg::kTile, NCH = BKV / 32;
+  pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;          // NST stages
+  uint8_t* sV = sK + NST * KV_TILE;       // NST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NST * KV_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;            // [NST]
+  uint64_t* k_empty = k_full + NST;       // [NST]
+  uint64_t* v_full = k_empty + NST;       // [NST]
+  uint64_t* v_empty = v_full + NST;       // [NST]
+  uint64_t* s_full = v_empty + NST;       // [2]  S_j complete in TMEM buffer j & 1
+  uint64_t* p_full = s_full + 2;          // [2]  P_j stored over S_j (4 arrivals: lane 0 of every softmax warp)
+  uint64_t* o_full = p_full + 2;          // O += P_j V_j retired (one phase per block)
+  uint64_t* o_final = o_full + 1;         // the last P V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * BQ;
+  const int kv_len = min(p.kv_len ? p.kv_len[b] : p.T, p.T);
+  int kv_end = kv_len;
+  if (p.causal) kv_end = min(kv_end, q0 + BQ);
+  const int n_kv = (kv_end + BKV - 1) / BKV;
+#if MH_F2_TRACE
+  // traced CTAs: query tile 2 of head 3 of batch items 0, 4, 8, ... 28 (spread over the launch); lane 0 of warp 0 / warp 5
+  const int trace_cta = (qb == 2 && h == 3 && (b & 3) == 0 && (b >> 2) < 8 && lane == 0) ? (b >> 2) : -1;
+  if (warp == 0) F2_STAMP(0, 63, 0);
+#endif
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tm_out);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); }
+    mbar_init(o_full, 1);
+    mbar_init(o_final, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;                // buffer i at + BKV i
+  const uint32_t tmem_o = tmem_base + Cfg::kOCol;   // 64 columns
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tm, q_full, h * HD, q0, b);
+      int st = 0, ph = 1;  // (waiting on the "previous" phase of a fresh barrier passes at once)
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&k_empty[st], ph);
+        mbar_expect_tx(&k_full[st], KV_TILE);
+        tma_load_3d(sK + st * KV_TILE, &tmKV, &k_full[st], p.E + h * HD, j * BKV, b);
+        mbar_wait(&v_empty[st], ph);
+        mbar_expect_tx(&v_full[st], KV_TILE);
+        tma_load_3d(sV + st * KV_TILE, &tmKV, &v_full[st], 2 * p.E + h * HD, j * BKV, b);
+        if (++st == NST) { st = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, false, false);
+      const uint32_t idesc_o = make_idesc_bf16(BQ, HD, false, true);  // A = P from TMEM, B = V MN-major
+      mbar_wait(q_full, 0);
+      int ks = 0, kph = 0;
+      auto issue_s = [&](int j) {
+        mbar_wait(&k_full[ks], kph);
+        tc_fence_after();
+        const uint32_t a = smem_u32(sQ), bk = smem_u32(sK + ks * KV_TILE);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_s + (j & 1) * BKV, make_sdesc(a + k * 32, 0, 1024), make_sdesc(bk + k * 32, 0, 1024), idesc_s, k > 0);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[j & 1]);
+        if (++ks == NST) { ks = 0; kph ^= 1; }
+      };
+      if (n_kv > 0) issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      int vs = 0, vph = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM (over S_j)
+        F2_STAMP(0, j, 5);
+        mbar_wait(&v_full[vs], vph);
+        tc_fence_after();
+        const uint32_t bv = smem_u32(sV + vs * KV_TILE);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_bf16_ts(tmem_o, tmem_s + (j & 1) * BKV + k * 8, make_sdesc(bv + k * 2048, KV_TILE, 1024), idesc_o,
+                       (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&v_empty[vs]);
+        umma_commit(o_full);
+        if (j + 1 == n_kv) umma_commit(o_final);
+        if (++vs == NST) { vs = 0; vph ^= 1; }
+        if (j + 2 < n_kv) issue_s(j + 2);  // overwrites P_j: ordered behind P_j V_j in the tensor pipe
+        F2_STAMP(0, j, 6);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread t owns query row t
+    const int r = threadIdx.x;
+    const int q = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float sc = p.scale_log2;
+    const bool use_drop = p.drop.thresh != 0;
+    const DropState ds(p.drop);
+    const float lg_scale = use_drop ? d2.lg_scale : 0.f;
+    const uint64_t row_id = (static_cast<uint64_t>(b) * p.H + h) * p.T + q;
+    const uint64_t chunks_per_row = (p.T + 31) >> 5;
+    uint32_t* keep_ptr = (use_drop && p.keep != nullptr && q < p.T)
+                             ? p.keep + (static_cast<long long>(b) * p.H + h) * p.keep_words * p.T + q
+                             : nullptr;
+    uint64_t drop_ctr = row_id * chunks_per_row * 4;  // Philox counter of (row, 32-key chunk, call t): + 4 chunk + t
+    const uint64_t sc2 = pack2f(sc, sc);
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ts = tmem_s + (j & 1) * BKV + lane_off;
+      F2_STAMP(0, j, 0);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      F2_STAMP(0, j, 1);
+      int lim = kv_len - j * BKV;  // keys [0, lim) of this block are visible to this row
+      if (p.causal) lim = min(lim, q - j * BKV + 1);
+      uint32_t pk[NCH][16];  // bf16 pairs of the block's probabilities
+      float l_blk;
+#pragma unroll 1
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        uint32_t s[NCH][32];
+#if MH_F2_KO & 8
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(static_cast<float>((r * 7 + i * 3 + j) & 15));
+#else
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld32(ts + c * 32, s[c]);
+        tmem_ld_wait();
+#endif
+        if (lim < BKV) {  // last (or diagonal) block only
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= lim) s[c][i] = 0xff800000u;  // -inf: probability 0
+        }
+        if (j == 0 || attempt == 1) {
+          // reference maximum of the row: first block, or a block that left the safe range of the old reference
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                m4[u] = fmax3(m4[u], __uint_as_float(s[c][i + 2 * u]), __uint_as_float(s[c][i + 2 * u + 1]));
+          const float m_blk = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+          if (attempt == 1) {
+            // rare: rescale what has been accumulated against the old reference (warp-uniform branch: tcgen05.ld /
+            // st are warp-collective; rows that did not overflow keep alpha = 1)
+            const bool need = !(l_blk < 1e30f) && m_blk > m_run;
+            const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;  // m_run = -inf -> 0
+            if (j > 0) {
+              mbar_wait(o_full, (j - 1) & 1);  // P_{j-1} V_{j-1} must have landed before O is touched
+              tc_fence_after();
+              rescale_o_rows(tmem_o + lane_off, alpha);
+            }
+            l_run *= alpha;
+            if (need) m_run = m_blk;
+          } else {
+            m_run = m_blk;
+          }
+        }
+        const float m_off = (m_run == -INFINITY ? 0.f : m_run) - lg_scale;
+        const uint64_t nm2 = pack2f(-m_off, -m_off);
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x0, x1;
+            unpack2f(ffma2(pack2f(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2), x0, x1);
+#if MH_F2_KO & 1
+            const float e0 = x0 * x0, e1 = x1 * x1;
+#else
+            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+#endif
+            acc[i & 3] = fadd2(acc[i & 3], pack2f(e0, e1));
+            pk[c][i] = pack_bf16(e0, e1);
+          }
+        }
+        float a0, a1;
+        unpack2f(fadd2(fadd2(acc[0], acc[1]), fadd2(acc[2], acc[3])), a0, a1);
+        l_blk = a0 + a1;
+        // a row sum anywhere near the fp32 / bf16 overflow range means this block's scores exceed the reference by
+        // > 2^90: raise the reference and redo the block (never taken with bounded activations)
+        if (attempt == 1 || !__any_sync(0xffffffffu, !(l_blk < 1e30f))) break;
+      }
+      l_run += l_blk;
+      F2_STAMP(0, j, 2);
+      if (use_drop) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t w[12];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#if MH_F2_KO & 2
+            const uint32_t cc = static_cast<uint32_t>(drop_ctr) + t;
+            const uint4 bits = make_uint4(cc * 0x9E3779B9u, cc ^ 0x12345u, cc + 77u, ~cc);
+#else
+            const uint4 bits = ds.bits(p.drop, drop_ctr + t);
+#endif
+            w[4 * t] = bits.x; w[4 * t + 1] = bits.y; w[4 * t + 2] = bits.z; w[4 * t + 3] = bits.w;
+          }
+          drop_ctr += 4;
+          // keep iff R >= thr (R = the 12-bit number whose bit k is plane k): compare from the least significant plane up
+          uint32_t ge = 0xffffffffu;
+#pragma unroll
+          for (int k = 0; k < 12; ++k)  // ge = t ? (w & ge) : (w | ge) -- one LOP3 per plane
+            asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(w[k]), "r"(d2.tmask[k]));
+          if (keep_ptr != nullptr && !(MH_F2_KO & 4)) {
+            *keep_ptr = ge;
+            keep_ptr += p.T;
+          }
+#pragma unroll
+          for (int sft = 0; sft < 8; ++sft) {
+            const uint32_t a = ge << sft;
+            pk[c][2 * sft] &= prmt_sel<0xBB99>(a);
+            pk[c][2 * sft + 1] &= prmt_sel<0xAA88>(a);
+          }
+        }
+      }
+      F2_STAMP(0, j, 3);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_st16(ts + c * 16, pk[c]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      F2_STAMP(0, j, 4);
+    }
+    if (n_kv > 0) {
+      mbar_wait(o_final, 0);
+      tc_fence_after();
+    } else {
+      mbar_wait(q_full, 0);  // the output tile is staged in the Q buffer: its (unused) load must have landed
+    }
+    // with the keep-scale s folded in: l_run = s * sum(e), O_tmem = s * sum(keep e v)  ->  out = O_tmem * s / l_run
+    const float inv = l_run > 0.f ? (use_drop ? d2.keep_scale : 1.f) / l_run : 0.f;
+    const uint32_t o_row = smem_u32(sQ) + r * 128;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t rr[32];
+      if (n_kv > 0) {
+        tmem_ld32(tmem_o + lane_off + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = 0u;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[g * 8 + i]) * inv;
+        sts128(o_row + (((c * 4 + g) ^ (r & 7)) << 4), f32_to_bf16x8(v));
+      }
+    }
+    fence_proxy_async_smem();
+    bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tm_out, sQ, h * HD, q0, b);
+      bulk_commit();
+      bulk_wait_read0();
+    }
+    if (q < p.T)
+      p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) - lg_scale : INFINITY;
+    tc_fence_before();
+#if MH_F2_TRACE
+    if (warp == 0) F2_STAMP(0, 63, 1);
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+#if MH_F2_TRACE
+  if (warp == 0) F2_STAMP(0, 63, 2);
+#endif
+}
+
 // ----------------------------------------------------------------------------- backward
 // delta[b,h,q] = sum_d dO[row, h*64+d] * O[row, h*64+d]: 8 lanes x 16 bytes per (row, head), coalesced.
 __global__ void __launch_bounds__(256)
@@ -382,6 +807,12 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   }
 }
 
+#if MH_ATTN_V1
+#define KEEP_POS keep_bit_pos
+#else
+#define KEEP_POS keep_bit_pos2
+#endif
+
 struct AttnBwdParams {
   const int* kv_len;
   const float* lse;     // base-2
@@ -394,6 +825,7 @@ struct AttnBwdParams {
   DropCfg drop;
   const uint32_t* keep;  // [B, H, keep_words, T] keep bits written by the forward (required when dropout is on)
   int keep_words;
+  float keep_scale;      // 1 / (1 - p) exactly as the forward applied it
 };
 
 // smem: K, V (16 KB each) | Q[3], dO[3] (96 KB) | P (32 KB) | dS (32 KB) | dQ staging [128 x 64] f32 (32 KB)
@@ -658,8 +1090,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const bool use_drop = p.drop.thresh != 0;
     // keep-scale s = 1/(1-p) folded into the exponent: pr' = s * P.  With u = keep ? dP : 0:
     //   P_drop = keep ? pr' : 0,   dS = P (s u - delta) c = pr' (c u - c delta / s)
-    const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
-    const float inv_s = (use_drop ? 1.f / p.drop.scale : 1.f) * p.scale;
+    const float lg_scale = use_drop ? log2f(p.keep_scale) : 0.f;
+    const float inv_s = (use_drop ? 1.f / p.keep_scale : 1.f) * p.scale;
     // this thread's 64 bytes of its P row (dS: + 2 tiles): atom (kc0 >> 6), row r, 16-byte chunks ch0 .. ch0 + 3
     const uint32_t p_row = smem_u32(sP) + (kc0 >> 6) * TILE_BYTES + r * 128;
     const int ch0 = (kc0 & 63) >> 3;
@@ -785,8 +1217,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
               uint32_t w4[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const uint32_t m = (((kbits >> keep_bit_pos(8 * g + 2 * t)) & 1u) ? 0x0000ffffu : 0u) |
-                                   (((kbits >> keep_bit_pos(8 * g + 2 * t + 1)) & 1u) ? 0xffff0000u : 0u);
+                const uint32_t m = (((kbits >> KEEP_POS(8 * g + 2 * t)) & 1u) ? 0x0000ffffu : 0u) |
+                                   (((kbits >> KEEP_POS(8 * g + 2 * t + 1)) & 1u) ? 0xffff0000u : 0u);
                 w4[t] = pk[4 * g + t] & m;
               }
               sts128(p_row + (((ch0 + g) ^ (r & 7)) << 4), make_uint4(w4[0], w4[1], w4[2], w4[3]));
@@ -814,7 +1246,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
               const uint32_t raw = (g & 1) ? db[t] : da[t];
-              const float u = ((kbits >> keep_bit_pos(8 * g + t)) & 1u) ? __uint_as_float(raw) : 0.f;
+              const float u = ((kbits >> KEEP_POS(8 * g + t)) & 1u) ? __uint_as_float(raw) : 0.f;
               const uint32_t pw = pk[4 * g + (t >> 1)];
               ds[t] = ((t & 1) ? bf16_hi(pw) : bf16_lo(pw)) * fmaf(u, p.scale, -dls);
             }
@@ -892,7 +1324,7 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   CUtensorMap tm, tmkv;
   int rc = make_tmap_3d(&tm, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, BQ);
   if (rc) return rc;
-  rc = make_tmap_3d(&tmkv, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, FBKV);
+  rc = make_tmap_3d(&tmkv, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, MH_ATTN_V1 ? FBKV : MH_F2_BKV);
   if (rc) return rc;
   CUtensorMap tmo;
   rc = make_tmap_3d(&tmo, out, E, T, B, E, static_cast<long long>(T) * E, HD, BQ);
@@ -900,6 +1332,7 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   static bool configured = false;
   if (!configured) {
     MH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    MH_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<MH_F2_BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Cfg<MH_F2_BKV>::kSmem));
     configured = true;
   }
   AttnParams p;
@@ -909,10 +1342,23 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   p.drop = make_drop(p_drop, seed, site);
   p.keep = reinterpret_cast<uint32_t*>(keep_bits);
   p.keep_words = ((T + 127) / 128) * 4;
+#if MH_ATTN_V1
   MH_CUDA(launch_pdl(attn_fwd_kernel, dim3((T + BQ - 1) / BQ, heads, B), dim3(192), FWD_SMEM, st, tm, tmkv, tmo, p));
+#else
+  MH_CUDA(launch_pdl(attn_fwd2_kernel<MH_F2_BKV>, dim3((T + BQ - 1) / BQ, heads, B), dim3(192), F2Cfg<MH_F2_BKV>::kSmem, st,
+                     tm, tmkv, tmo, p, make_drop2(p_drop)));
+#endif
   ++g_launches;
   return 0;
 }
+
+#if MH_F2_TRACE
+extern "C" int mh_attn_trace_read(long long* host_out) {  // debug builds only: 8 x 64 x 8 clock64 stamps
+  MH_CUDA(cudaDeviceSynchronize());
+  MH_CUDA(cudaMemcpyFromSymbol(host_out, g_f2_trace, sizeof(long long) * 8 * 64 * 8));
+  return 0;
+}
+#endif
 
 extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                            const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
@@ -954,6 +1400,11 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   p.drop = make_drop(p_drop, seed, site);
   p.keep = reinterpret_cast<const uint32_t*>(keep_bits);
   p.keep_words = ((T + 127) / 128) * 4;
+#if MH_ATTN_V1
+  p.keep_scale = p.drop.scale;
+#else
+  p.keep_scale = make_drop2(p_drop).keep_scale;
+#endif
   {
     const long long items = static_cast<long long>((T + BKV - 1) / BKV) * heads * B;
     MH_CHECK(items < (1LL << 31), "attn_bwd: too many work items");

@@ -82,7 +82,11 @@ class BasePruningMethod:
         weight = self.apply_mask(module)
         module._buffers.pop(name, None)
         orig = module._parameters.pop(name + "_orig")
-        orig.data = weight.data
+        # in place: the Parameter's storage is a view into the flat parameter buffer the fused optimizer
+        # updates (parallel.FlatBuffers); re-pointing ``orig.data`` (what torch.nn.utils.prune does) would
+        # orphan that slot and silently freeze the tensor
+        with torch.no_grad():
+            orig.data.copy_(weight.detach())
         del module._buffers[name + "_mask"]
         module.register_parameter(name, orig)
 

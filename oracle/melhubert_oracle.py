@@ -99,11 +99,11 @@ def attention(x, sd, prefix, key_pad, causal=False):
     k = (x @ wk.t() + bk).view(B, T, heads, HEAD_DIM).transpose(1, 2)
     v = (x @ wv.t() + bv).view(B, T, heads, HEAD_DIM).transpose(1, 2)
     s = (q / math.sqrt(HEAD_DIM)) @ k.transpose(-1, -2)  # (B, h, T, T)
-    neg = torch.zeros(B, 1, 1, T)
+    neg = torch.zeros(B, 1, 1, T, device=x.device)  # fp32 additive mask (forward_multihead_attention.py:221)
     neg.masked_fill_(key_pad.view(B, 1, 1, T), float("-inf"))
     s = s + neg
     if causal:
-        tri = torch.ones(T, T, dtype=torch.bool).triu(1)
+        tri = torch.ones(T, T, dtype=torch.bool, device=x.device).triu(1)
         s = s.masked_fill(tri, float("-inf"))
     p = torch.softmax(s, dim=-1)
     ctx = (p @ v).transpose(1, 2).reshape(B, T, heads * HEAD_DIM)

@@ -1190,6 +1190,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         // fp32 copies cost 16 more registers than the 96 a 19-warp CTA leaves per thread (spills in the hot loop)
         uint32_t pk[16];
         // ---- phase A: P = exp2(S c - lse), P_drop (bf16) -> smem
+        // Instruction diet (the kernel is issue-bound: 19 executed instructions per score before, ncu): the exponent
+        // argument is one packed FFMA2 per two scores, and the dropped keys are zeroed with the 16-bit pair masks that
+        // two PRMTs derive from one shifted copy of the keep word (keep_bit_pos2 layout) instead of per-bit tests.
         if (n == 0 && cnt > 0) mbar_wait(kv_st_free, (cnt - 1) & 1);  // previous item's dK / dV left the P / dS tiles
         mbar_wait(s_full, it & 1);
         tc_fence_after();
@@ -1198,30 +1201,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           tmem_ld16(tm_s + lane_off + kc0, sa);
           tmem_ld_wait();
           tmem_ld16(tm_s + lane_off + kc0 + 16, sb);  // in flight under the first half's exponentials
+          const uint64_t sc2 = pack2f(p.scale_log2, p.scale_log2), nl2 = pack2f(-lse, -lse);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             if (half == 1) tmem_ld_wait();
-            float pr[16];
+            uint32_t(&src)[16] = half == 0 ? sa : sb;
+            if (rem0 < 32) {  // last / diagonal key block only: -inf -> probability 0
 #pragma unroll
-            for (int t = 0; t < 16; ++t)
-              pr[t] = ex2_approx(fmaf(__uint_as_float(half == 0 ? sa[t] : sb[t]), p.scale_log2, -lse));
-            if (rem0 < 32) {
-#pragma unroll
-              for (int t = 0; t < 16; ++t) pr[t] = 16 * half + t < rem0 ? pr[t] : 0.f;
+              for (int t = 0; t < 16; ++t)
+                if (16 * half + t >= rem0) src[t] = 0xff800000u;
             }
 #pragma unroll
-            for (int t = 0; t < 8; ++t) pk[8 * half + t] = pack_bf16(pr[2 * t], pr[2 * t + 1]);
+            for (int t = 0; t < 8; ++t) {
+              float x0, x1;
+              unpack2f(ffma2(pack2f(__uint_as_float(src[2 * t]), __uint_as_float(src[2 * t + 1])), sc2, nl2), x0, x1);
+              pk[8 * half + t] = pack_bf16(ex2_approx(x0), ex2_approx(x1));
+            }
 #pragma unroll
             for (int g = 2 * half; g < 2 * half + 2; ++g) {
-              // dropped keys: zero the 16-bit halves of the packed pairs
-              uint32_t w4[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const uint32_t m = (((kbits >> KEEP_POS(8 * g + 2 * t)) & 1u) ? 0x0000ffffu : 0u) |
-                                   (((kbits >> KEEP_POS(8 * g + 2 * t + 1)) & 1u) ? 0xffff0000u : 0u);
-                w4[t] = pk[4 * g + t] & m;
-              }
-              sts128(p_row + (((ch0 + g) ^ (r & 7)) << 4), make_uint4(w4[0], w4[1], w4[2], w4[3]));
+              // pairs 4 g .. 4 g + 3 = shifts s = 2 g, 2 g + 1 of the keep word (see keep_pair_masks)
+              const uint32_t k0 = kbits << (2 * g), k1 = kbits << (2 * g + 1);
+              sts128(p_row + (((ch0 + g) ^ (r & 7)) << 4),
+                     make_uint4(pk[4 * g] & prmt_sel<0xBB99>(k0), pk[4 * g + 1] & prmt_sel<0xAA88>(k0),
+                                pk[4 * g + 2] & prmt_sel<0xBB99>(k1), pk[4 * g + 3] & prmt_sel<0xAA88>(k1)));
             }
           }
         }
@@ -1232,25 +1234,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         // ---- dQ of the previous query block (its MMA ran under phase A)
         if (n > 0) drain_dq(it - 1);
         // ---- phase B: dS = P (c u - c delta / s), bf16 -> smem
+        // u = keep ? dP : 0 as a bitwise AND with 32-bit masks (one PRMT each: the sign of byte 1 / 3 / 0 / 2 of the
+        // shifted keep word replicated over the word), then packed fp32: FFMA2 (c u - c delta / s), FMUL2 (x P).
         mbar_wait(dp_full, it & 1);
         tc_fence_after();
         {
           uint32_t da[8], db[8];
           tmem_ld8(tm_dp + lane_off + kc0, da);
           tmem_ld_wait();
+          const uint64_t c2 = pack2f(p.scale, p.scale), nd2 = pack2f(-dls, -dls);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             // the next group's dP is in flight while this one is turned into dS
             if (g + 1 < 4) tmem_ld8(tm_dp + lane_off + kc0 + (g + 1) * 8, (g & 1) ? da : db);
-            float ds[8];
+            uint32_t(&raw)[8] = (g & 1) ? db : da;
+            uint32_t dsw[4];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const uint32_t raw = (g & 1) ? db[t] : da[t];
-              const float u = ((kbits >> KEEP_POS(8 * g + t)) & 1u) ? __uint_as_float(raw) : 0.f;
-              const uint32_t pw = pk[4 * g + (t >> 1)];
-              ds[t] = ((t & 1) ? bf16_hi(pw) : bf16_lo(pw)) * fmaf(u, p.scale, -dls);
+            for (int j = 0; j < 4; ++j) {  // pair 4 g + j: elements 8 g + 2 j (low half), 8 g + 2 j + 1 (high half)
+              const uint32_t ks = kbits << (2 * g + (j >> 1));
+              const uint32_t u0 = raw[2 * j] & ((j & 1) ? prmt_sel<0x8888>(ks) : prmt_sel<0x9999>(ks));
+              const uint32_t u1 = raw[2 * j + 1] & ((j & 1) ? prmt_sel<0xAAAA>(ks) : prmt_sel<0xBBBB>(ks));
+              const uint32_t pw = pk[4 * g + j];
+              float d0, d1;
+              unpack2f(fmul2(pack2f(bf16_lo(pw), bf16_hi(pw)),
+                             ffma2(pack2f(__uint_as_float(u0), __uint_as_float(u1)), c2, nd2)), d0, d1);
+              dsw[j] = pack_bf16(d0, d1);
             }
-            sts128(p_row + 2 * TILE_BYTES + (((ch0 + g) ^ (r & 7)) << 4), f32_to_bf16x8(ds));
+            sts128(p_row + 2 * TILE_BYTES + (((ch0 + g) ^ (r & 7)) << 4), make_uint4(dsw[0], dsw[1], dsw[2], dsw[3]));
             if (g + 1 < 4) tmem_ld_wait();
           }
         }

@@ -104,7 +104,12 @@ class MelHuBERTDistiller(nn.Module):
                 C = s_h.shape[-1]
                 loss = loss + ops.l1_cosine_loss(_rows_bf16(s_h),
                                                  _rows_bf16(t_h.detach()), self.cos_weight)
-            return loss / max(len(self.layer_map), 1), 1
+            loss = loss / max(len(self.layer_map), 1)
+            if self.dp is not None and self.dp.enabled:
+                # a per-rank frame mean: the bucket all-reduce SUMS gradients over ranks, so the 1 / world that makes
+                # them the global mean (CE / KD get it through their global frame count) is applied here
+                loss = loss / self.dp.world_size
+            return loss, 1
         if self.loss_type == "masked":
             total, h, s, t = self.loss_fn_kd(s_out[1], s_out[3], t_out[1], T=self.loss_temp, alpha=self.loss_alpha)
         else:

@@ -12,6 +12,7 @@ import os
 import torch
 from tqdm import tqdm
 
+from .. import ckpt
 from .. import kernels as K
 from ..fairseq_code import MultiheadAttention
 from ..surgery import drop_heads
@@ -76,7 +77,7 @@ class HeadPruningTools:
     def prune(self):
         n_to_prune = self.num_heads_each_step
         heads_and_score = self.get_heads_norm(self.upstream.model.encoder)
-        torch.save(heads_and_score, os.path.join(self.args.expdir, f"heads_and_score_{self.total_heads}.ckpt"))
+        ckpt.save(heads_and_score, os.path.join(self.args.expdir, f"heads_and_score_{self.total_heads}.ckpt"))
         ranked = [hs[0] for hs in sorted(heads_and_score, key=lambda x: x[1])]  # stable, ascending score
         target = self.runner_config["prune"]["target"]
         if target == "by_whole":
@@ -124,4 +125,4 @@ class HeadPruningTools:
         path = os.path.join(self.args.expdir, f"states_prune_{self.total_heads}.ckpt")
         tqdm.write(f"[Head Pruning] - Save the checkpoint to: {path}")
         tqdm.write("[Head Pruning] - Number of parameters saved: " + str(sum(p.numel() for p in states["model"].values())))
-        torch.save(states, path)
+        ckpt.save(states, path)

@@ -90,6 +90,7 @@ class DataParallelB200:
         self.flat = None
         self._pending = []
         self._comm_stream = None
+        self.sync = True  # False while a non-final micro-batch of a gradient-accumulation step runs (no all-reduce)
 
     # -- loss normaliser ---------------------------------------------------------------------
     def all_reduce_sum(self, t):
@@ -101,6 +102,10 @@ class DataParallelB200:
     def attach(self, flat: FlatBuffers):
         """Register the flat gradient buffer and hook every encoder layer's backward."""
         self.flat = flat
+        if self.enabled and float(getattr(self.model.encoder, "layerdrop", 0.0) or 0.0) > 0.0:
+            # a layer skipped by its host-side draw (module.py:243) issues no bucket all-reduce: ranks whose draws
+            # differ would post mismatched collectives and hang
+            raise RuntimeError("encoder_layerdrop > 0 is not supported with data parallelism")
         if self.enabled:  # identical start on every rank: one broadcast of the whole flat parameter buffer
             dist.broadcast(flat.flat_param, src=0)
         self._layer_spans = []
@@ -123,7 +128,7 @@ class DataParallelB200:
             self._comm_stream = torch.cuda.Stream()
 
     def _reduce_span(self, span):
-        if not self.enabled or span is None:
+        if not self.enabled or span is None or not self.sync:
             return
         buf = self.flat.flat_grad[span[0]:span[1]]
         if self._comm_stream is not None and self.overlap:
@@ -140,6 +145,8 @@ class DataParallelB200:
 
     def finish(self):
         """All-reduce the non-layer remainder and join the communication stream."""
+        if not self.sync:
+            return
         for span in self._rest_spans:
             self._reduce_span(span)
         if self._comm_stream is not None:

@@ -10,6 +10,7 @@ import os
 import torch
 from tqdm import tqdm
 
+from .. import ckpt
 from .. import kernels as K
 from ..head_pruning.hp_utils import set_prune_interval  # noqa: F401  (same helper in the reference)
 from ..surgery import drop_ffn_rows
@@ -57,4 +58,4 @@ class RowPruningTools:
         path = os.path.join(self.args.expdir, f"states_prune_{self.total_ffn_dim}.ckpt")
         tqdm.write(f"[Row Pruning] - Save the checkpoint to: {path}")
         tqdm.write("[Row Pruning] - Number of parameters saved: " + str(sum(p.numel() for p in states["model"].values())))
-        torch.save(states, path)
+        ckpt.save(states, path)

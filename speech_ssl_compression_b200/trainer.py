@@ -28,6 +28,7 @@ class FusedAdam:
         self.shadow = flat.enable_shadow() if flat.flat_param.is_cuda else None
         self.step_count = torch.zeros(1, device=flat.flat_param.device, dtype=torch.int64)
         self.sumsq = torch.zeros(1, device=flat.flat_param.device, dtype=torch.float32)
+        self.param_order = None  # all parameters the reference would hand to Adam, in its order (set by TrainStep)
 
     def step(self, grad_scale=1.0, max_norm=0.0):
         K.counter_add(self.step_count, 1)
@@ -46,13 +47,52 @@ class FusedAdam:
         self.flat.flat_grad.zero_()
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
-                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+        """``torch.optim.Adam.state_dict()`` layout (what the reference stores under ``"Optimizer"``, runner.py:154-172,
+        mh_utils.py:17): ``state[i] = {step, exp_avg, exp_avg_sq}`` with i the parameter's position in
+        ``param_order`` (the expert's ``parameters()`` order -- frozen parameters hold an index but no state, exactly
+        like gradient-less parameters in torch), one param group."""
+        order = self.param_order if self.param_order is not None else self.flat.params
+        slot = {id(p): (o, p) for p, o in zip(self.flat.params, self.flat.offsets)}
+        state = {}
+        step = self.step_count.to(torch.float32).reshape(()).cpu()
+        if float(step) > 0:
+            for i, p in enumerate(order):
+                if id(p) in slot:
+                    o = slot[id(p)][0]
+                    state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape).clone(),
+                                "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(order)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.step_count.copy_(sd["step"])
+        """Accepts the torch layout above (also a checkpoint written by the reference's ``torch.optim.Adam``) and the
+        flat layout of this class's first version.  Shapes must match the current parameters."""
+        if "param_groups" not in sd:
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.step_count.copy_(sd["step"])
+            return
+        order = self.param_order if self.param_order is not None else self.flat.params
+        if len(sd["param_groups"][0]["params"]) != len(order):
+            raise ValueError(f"optimizer state holds {len(sd['param_groups'][0]['params'])} parameters, the model has {len(order)}")
+        slot = {id(p): o for p, o in zip(self.flat.params, self.flat.offsets)}
+        step = 0
+        for i, st in sd["state"].items():
+            p = order[int(i)]
+            if id(p) not in slot:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} != parameter {tuple(p.shape)}")
+            o = slot[id(p)]
+            self.exp_avg[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+            step = max(step, int(float(st["step"])))
+        self.step_count.fill_(step)
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.weight_decay = float(g["weight_decay"])
 
 
 def trainable_params(expert):
@@ -95,8 +135,13 @@ class TrainStep:
     per-layer layer-drop draws that shift the stream)."""
 
     def __init__(self, expert, B, T, D, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=10.0,
-                 use_graph=True, device="cuda"):
+                 use_graph=True, device="cuda", accum=1):
         self.expert, self.B, self.T, self.D = expert, B, T, D
+        # gradient accumulation (runner.py:370-371, :396-399): ``accum`` micro-batches per optimizer step.  The wgrad
+        # kernels add into the flat gradient buffer, so a micro-batch is one more forward + backward; the 1/accum of
+        # ``loss / gradient_accumulate_steps`` is applied once, as the fused Adam step's grad_scale.
+        self.accum = max(int(accum), 1)
+        self._micro = 0
         self.device = torch.device(device)
         self.max_norm = max_norm
         self.model = expert.model
@@ -106,6 +151,7 @@ class TrainStep:
             self.teacher.static_rows = True
         self.flat = FlatBuffers(trainable_params(expert))
         self.opt = FusedAdam(self.flat, lr, betas, eps, weight_decay)
+        self.opt.param_order = list(expert.parameters())  # runner.py:314 Adam(expert.parameters())
         self.dp = getattr(expert, "dp", None)
         if self.dp is not None:
             self.dp.attach(self.flat)
@@ -121,11 +167,12 @@ class TrainStep:
         self.pad = torch.ones(B, T, device=dev)
         self.mask = torch.zeros(B, T, device=dev, dtype=torch.bool)
         self.loss = torch.zeros(1, device=dev)
+        self.loss_acc = torch.zeros(1, device=dev)  # sum of the micro-batch losses of the step in flight
         self.h_loss = torch.zeros(1).pin_memory()
         self.rng_counter = torch.zeros(1, device=dev, dtype=torch.int64)
         K.set_dropout_offset(self.rng_counter)
         self.use_graph = use_graph
-        self.graph = None
+        self.graphs = None  # {False: forward + backward of a non-final micro-batch, True: final micro-batch + optimizer}
         self.n_layerdrop_draws = self.model.model_config.encoder_layers + (
             self.teacher.model_config.encoder_layers if self.teacher is not None else 0)
         self.h2d_bytes = self.d2h_bytes = 0
@@ -214,19 +261,31 @@ class TrainStep:
         ev.synchronize()
         return float(buf[0])
 
-    def _body(self):
+    def _body(self, last=True):
+        """One micro-batch: forward + backward into the flat gradient buffer.  ``last``: also the gradient
+        all-reduce, the loss mean over the step's micro-batches and clip + Adam (+ zero_grad)."""
         K.counter_add(self.rng_counter, 1)
         data = (self.feat, self.label, self.pad, None)
+        if self.dp is not None:
+            self.dp.sync = last  # bucket all-reduces only behind the final micro-batch's backward
         self._patch_mask(True)
         try:
             loss, _ = self.expert(data)
         finally:
             self._patch_mask(False)
         loss.backward()
+        loss = loss.detach().reshape(1)
+        if not last:
+            self.loss_acc.add_(loss)
+            return
         if self.dp is not None:
             self.dp.finish()
-        self.loss.copy_(loss.detach().reshape(1))
-        self.opt.step(grad_scale=1.0, max_norm=self.max_norm)
+        if self.accum > 1:
+            self.loss.copy_((self.loss_acc + loss) / self.accum)
+            self.loss_acc.zero_()
+        else:
+            self.loss.copy_(loss)
+        self.opt.step(grad_scale=1.0 / self.accum, max_norm=self.max_norm)
 
     def _patch_mask(self, on):
         """Feed the pre-drawn device mask through the model's ``teacher_mask_indices`` door so no
@@ -239,39 +298,71 @@ class TrainStep:
         else:
             first._draw_mask = self._orig_draw
 
+    def _snapshot(self):
+        o, f = self.opt, self.flat
+        t = [f.flat_param, f.flat_grad, o.exp_avg, o.exp_avg_sq, o.step_count, o.sumsq, self.rng_counter, self.loss,
+             self.loss_acc]
+        if f.flat_bf16 is not None:
+            t.append(f.flat_bf16)
+        return [(x, x.clone()) for x in t], np.random.get_state()
+
+    @staticmethod
+    def _restore(snap):
+        for x, c in snap[0]:
+            x.copy_(c)
+        np.random.set_state(snap[1])
+
     def capture(self, warmup=2):
-        """Warm up eagerly on a side stream, then capture one step into a CUDA graph."""
+        """Warm up eagerly on a side stream, then capture the step into CUDA graphs (one for a non-final micro-batch when
+        accumulating, one for the final micro-batch + optimizer).  The warm-up runs real optimizer steps on whatever
+        batch is loaded, so parameters, Adam state, step / dropout counters and the NumPy stream are put back afterwards:
+        capturing changes nothing the training run can see."""
+        snap = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self._body()
+                if self.accum > 1:
+                    self._body(False)
+                self._body(True)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._restore(snap)
         ops.bump_weight_epoch()  # operand prep of masked / non-flat weights must be part of the captured step
-        self.flat._shadow_epoch = ops._EPOCH[0]  # (the bf16 shadow is current: written by the warm-up Adam steps)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = K.L.launch_count()
-        rng_state = np.random.get_state()  # the per-layer layer-drop draws of the captured forward are replayed
-        with torch.cuda.graph(self.graph):  # by run(); capturing must not advance the host stream
-            self._body()
-        np.random.set_state(rng_state)
-        self.launches_per_step = K.L.launch_count() - n0
+        self.flat._shadow_epoch = ops._EPOCH[0]  # (the bf16 shadow is current: restored with the parameters)
+        self.graphs, self.launches = {}, {}
+        pool = torch.cuda.graph_pool_handle()
+        for last in ((False, True) if self.accum > 1 else (True,)):
+            g = torch.cuda.CUDAGraph()
+            n0 = K.L.launch_count()
+            with torch.cuda.graph(g, pool=pool):  # capturing executes nothing on the device ...
+                self._body(last)
+            self.graphs[last], self.launches[last] = g, K.L.launch_count() - n0
+            ops.bump_weight_epoch()  # each graph carries its own operand prep of non-shadow weights
+            self.flat._shadow_epoch = ops._EPOCH[0]
+        np.random.set_state(snap[1])  # ... but the per-layer layer-drop draws of the captured forwards advanced the host stream
+        self.launches_per_step = self.launches[True] + (self.accum - 1) * self.launches.get(False, 0)
         return self
 
     def run(self):
-        """Execute one optimizer step on the currently loaded batch; returns nothing (loss is in
-        ``self.loss`` on the device; ``read_loss`` fetches it)."""
+        """Execute one micro-batch on the currently loaded batch; every ``accum``-th call is the final one of an
+        optimizer step (returns True then).  The loss of a finished step (mean over its micro-batches) is in
+        ``self.loss`` on the device; ``read_loss`` / ``read_loss_async`` fetch it."""
+        last = (self._micro + 1) % self.accum == 0
+        self._micro += 1
         if self.use_graph:
-            if self.graph is None:
+            if self.graphs is None:
                 self.capture()
             for _ in range(self.n_layerdrop_draws):
                 np.random.random()  # a replay skips the per-layer host draws of the eager forward (module.py:243)
-            self.graph.replay()
+            self.graphs[last].replay()
         else:
             n0 = K.L.launch_count()
-            self._body()
-            self.launches_per_step = K.L.launch_count() - n0
+            self._body(last)
+            n = K.L.launch_count() - n0
+            self.launches_per_step = n if self.accum == 1 else (n + getattr(self, "_micro_launches", 0) if last else 0)
+            self._micro_launches = 0 if last else getattr(self, "_micro_launches", 0) + n
+        return last
 
     def read_loss(self):
         self.h_loss.copy_(self.loss, non_blocking=True)

@@ -5,6 +5,8 @@ import os
 import torch
 from tqdm import tqdm
 
+from ... import ckpt
+
 
 class MelHuBERTTools:
     def __init__(self, args, runner_config, upstream_config, upstream):
@@ -21,4 +23,4 @@ class MelHuBERTTools:
         states = self.upstream.add_state_to_save(states)
         path = os.path.join(self.args.expdir, name or f"checkpoint-epoch-{num_epoch}.ckpt")
         tqdm.write(f"[MelHuBERT] - Save the checkpoint to: {path}")
-        torch.save(states, path)
+        ckpt.save(states, path)

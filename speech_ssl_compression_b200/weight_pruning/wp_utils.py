@@ -12,6 +12,7 @@ import numpy as np
 import torch
 from tqdm import tqdm
 
+from .. import ckpt
 from .. import ops
 from ..pytorch_code import prune
 
@@ -123,4 +124,4 @@ class WeightPruningTools:
         states = self.upstream.add_state_to_save(states)
         path = os.path.join(self.args.expdir, filename)
         tqdm.write(f"[Weight Pruning] - Save the checkpoint to: {path}")
-        torch.save(states, path)
+        ckpt.save(states, path)

@@ -249,3 +249,68 @@ def test_flac_decoder_known_answer():
     for fn, (md5, n) in want.items():
         pcm, sr, ok, hexd = decode_flac(os.path.join(ROOT, "tests", "golden", "example", fn))
         assert ok and hexd == md5 and sr == 16000 and len(pcm) == n
+
+
+# ------------------------------------------------------------------------------------ training-loop host logic
+def test_fused_adam_state_dict_is_the_torch_adam_layout():
+    """The checkpoint's ``"Optimizer"`` entry (runner.py:154-172, mh_utils.py:17) is ``torch.optim.Adam.state_dict()``
+    over ``expert.parameters()``: same keys, indices and shapes as torch writes, frozen parameters hold an index but
+    no state, and a torch-written state dict loads into the flat moment buffers (resume, runner.py:163-170)."""
+    from speech_ssl_compression_b200.parallel import FlatBuffers
+    from speech_ssl_compression_b200.trainer import FusedAdam
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    for p in net[1].parameters():
+        p.requires_grad_(False)  # (the distillation teacher)
+    ref = torch.optim.Adam(net.parameters(), lr=3e-4, betas=(0.8, 0.95), eps=1e-7)
+    for _ in range(3):
+        net(torch.randn(4, 6)).sum().backward()
+        ref.step()
+        ref.zero_grad()
+    want = ref.state_dict()
+    train = [p for p in net.parameters() if p.requires_grad]
+    opt = FusedAdam(FlatBuffers(train[::-1]), lr=1.0)  # flat order differs from parameters() order on purpose
+    opt.param_order = list(net.parameters())
+    opt.load_state_dict(want)
+    assert (opt.lr, opt.betas, opt.eps) == (3e-4, (0.8, 0.95), 1e-7) and int(opt.step_count) == 3
+    got = opt.state_dict()
+    assert set(got) == {"state", "param_groups"} and sorted(got["state"]) == sorted(want["state"]) == [0, 1, 4, 5]
+    assert got["param_groups"][0]["params"] == want["param_groups"][0]["params"] == list(range(6))
+    for i, st in want["state"].items():
+        assert set(got["state"][i]) == {"step", "exp_avg", "exp_avg_sq"} and float(got["state"][i]["step"]) == 3
+        assert torch.equal(got["state"][i]["exp_avg"], st["exp_avg"])
+        assert torch.equal(got["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+    again = torch.optim.Adam(net.parameters())
+    again.load_state_dict(got)  # and torch accepts what we write
+    with pytest.raises(ValueError):
+        opt.param_order = opt.param_order[:-1]
+        opt.load_state_dict(want)
+
+
+def test_bucket_dataset_is_sharded_by_rank(tmp_path):
+    """Data parallelism must add batch, not repeat it: ranks walk disjoint, equally sized shards of one bucket
+    permutation (the reference's DataParallel scatters one batch over the devices, pretrain_expert.py:28-30)."""
+    import pandas as pd
+
+    import runner
+
+    rows = []
+    for i in range(22):
+        n = 80 + 3 * i  # >= 40 stacked 20 ms frames: every utterance is cropped to sequence_length
+        np.save(tmp_path / f"f{i}.npy", np.full((n, 40), float(i), dtype=np.float32))
+        np.save(tmp_path / f"l{i}.npy", np.arange(n) % 7)
+        rows.append((str(tmp_path / f"f{i}.npy"), str(tmp_path / f"l{i}.npy"), n))
+    pd.DataFrame(rows, columns=["file_path", "label_path", "length"]).to_csv(tmp_path / "set.csv", index=False)
+    datarc, task = {"sets": [str(tmp_path / "set.csv")]}, {"sequence_length": 30}
+    seen = []
+    for rank in range(2):
+        torch.manual_seed(1337)
+        ds = runner.CsvNpyBuckets(datarc, task, 20, 2, rank=rank, world=2)
+        assert len(ds) == 5  # 11 buckets -> 5 per rank, the odd one is dropped so the ranks stay in step
+        ids = []
+        for feat, label, pad, lens in ds:
+            assert feat.shape == (2, 30, 80) and label.shape == (2, 30) and lens == [30, 30]
+            ids.append(tuple(sorted({int(feat[j, 0, 0]) for j in range(2)})))
+        seen.append(ids)
+    assert len(seen[0]) == len(seen[1]) == 5 and not set(seen[0]) & set(seen[1])

@@ -33,12 +33,13 @@ def test_extract_feature_cli_matches_reference_golden(golden):
     np.testing.assert_allclose(mel[:, ::9, ::7].numpy(), g["mel_f32_sub"], rtol=1e-5, atol=1e-5)
 
 
-def _write_cfgs(tmp, mode, layers=2):
+def _write_cfgs(tmp, mode, layers=2, accum=1):
     model = {"melhubert": dict(feat_emb_dim=80, encoder_layers=layers, encoder_embed_dim=768, encoder_ffn_embed_dim=3072,
                                encoder_attention_heads=12, num_cluster=512, mask_prob=0.7, mask_length=5, skip_masked=False,
                                skip_nomask=True, dropout=0.1, attention_dropout=0.1, activation_dropout=0.1),
              "task": {"sequence_length": 256}}
-    runner = {"runner": {"total_steps": 6, "log_step": 2, "gradient_clipping": 10.0, "save_every_x_epochs": 1},
+    runner = {"runner": {"total_steps": 6, "log_step": 2, "gradient_clipping": 10.0, "save_every_x_epochs": 1,
+                         "gradient_accumulate_steps": accum},
               "optimizer": {"lr": 1e-4, "betas": [0.9, 0.999], "eps": 1e-8, "weight_decay": 0},
               "datarc": {"train_batch_size": 2}}
     if mode == "row-pruning":
@@ -80,6 +81,29 @@ def test_train_cli_runs_each_mode_and_writes_reference_checkpoints(tmp_path, mod
         assert abs(pruned / total - 0.4) < 1e-3
     losses = [float(r.split(",")[2]) for r in open(os.path.join(exp, "train_log.csv")).read().strip().splitlines()]
     assert len(losses) == 3 and all(np.isfinite(losses))
+    # "Optimizer" is a torch.optim.Adam state dict over expert.parameters() (runner.py:154-172)
+    opt = st["Optimizer"]
+    assert set(opt) == {"state", "param_groups"} and float(opt["state"][0]["step"]) > 0
+
+
+def test_train_cli_gradient_accumulation_and_optimizer_resume(tmp_path):
+    """``gradient_accumulate_steps: 2``: 6 optimizer steps = 12 micro-batches (graph-captured pair of graphs); then
+    ``-i last-step.ckpt --init_optimizer_from_initial_weight`` restores the Adam moments (runner.py:163-170)."""
+    import train
+
+    mp, rp = _write_cfgs(str(tmp_path), "melhubert", accum=2)
+    exp = str(tmp_path / "exp")
+    train.main(["-m", "melhubert", "-g", mp, "-c", rp, "-n", exp, "-f", "20", "--synthetic"])
+    ck = os.path.join(exp, "last-step.ckpt")
+    st = torch.load(ck, map_location="cpu", weights_only=False)
+    assert st["Step"] == 6 and float(st["Optimizer"]["state"][0]["step"]) == 6
+    rows = open(os.path.join(exp, "train_log.csv")).read().strip().splitlines()
+    assert [int(r.split(",")[0]) for r in rows] == [2, 4, 6]
+    exp2 = str(tmp_path / "exp2")
+    train.main(["-m", "melhubert", "-g", mp, "-c", rp, "-n", exp2, "-f", "20", "--synthetic", "-i", ck,
+                "--init_optimizer_from_initial_weight", "--max_steps", "2"])
+    st2 = torch.load(os.path.join(exp2, "last-step.ckpt"), map_location="cpu", weights_only=False)
+    assert float(st2["Optimizer"]["state"][0]["step"]) == 8
 
 
 def test_train_cli_distillation(tmp_path):

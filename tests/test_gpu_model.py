@@ -10,6 +10,7 @@ hidden states rel-L2 <= 2e-2 after 12 layers, loss |delta| <= 2e-2, gradients re
 Span masks, label gathers and prune selections are bit-exact.
 """
 import copy
+import hashlib
 import os
 import tempfile
 from argparse import Namespace
@@ -127,8 +128,6 @@ def test_train_step_matches_reference_golden(golden, fwd20):
 
 
 # ------------------------------------------------------------------- cfg3's shape: 10 ms frames
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: first hardware run pending "
-                                        "(the CPU oracle is pinned against the same golden in tests/test_oracle_golden.py)")
 def test_10ms_eval_and_train_step_match_reference_golden(golden):
     """D_in = 40, 1500 frames, mask spans of 10 (12 attention key blocks per row, K = 40 pre-projection GEMM)."""
     from speech_ssl_compression_b200 import ops
@@ -355,9 +354,25 @@ def test_weight_pruning_masks_forward_and_masked_gradients(golden):
         # per-tensor counts are exact up to which members of a tie set at the threshold are taken
         # (torch.topk's tie order is implementation defined); totals are exact.
         assert sum(counts) == int(g[tag + "_counts"].sum())
-        diff = np.abs(np.array(counts) - g[tag + "_counts"])
-        assert diff.sum() <= 8, diff.sum()
         assert st[names[0] + "_mask"].dtype == torch.bool
+        # Bit-exact against the reference's masks (golden hashes of np.packbits(mask), generated by running the
+        # unmodified reference): every tensor that holds no element of the tie set {|w| == threshold} must have
+        # exactly the reference's mask; inside the tie set only the count is defined.  The radix-select threshold
+        # itself is checked too: everything pruned is <= tau, everything newly kept is >= tau.
+        mags = [st[n + "_orig"].detach().abs() for n in names]
+        pruned = [~st[n + "_mask"] for n in names]
+        tau = max(float(a[p].max()) for a, p in zip(mags, pruned) if bool(p.any()))
+        assert all(float(a[~p].min()) >= tau for a, p in zip(mags, pruned) if bool((~p).any()))
+        has_tie = [bool((a == tau).any()) for a in mags]
+        n_ties = sum(int((a == tau).sum()) for a in mags)
+        hashes = [hashlib.sha256(np.packbits(p.logical_not().cpu().numpy()).tobytes()).hexdigest()[:16] for p in pruned]
+        want = [str(x) for x in g[tag + "_hashes"]]
+        wrong = [n for n, h, w, t in zip(names, hashes, want, has_tie) if h != w and not t]
+        assert not wrong, f"{tag}: masks differ from the reference outside the tie set: {wrong[:4]}"
+        if n_ties <= 1:
+            assert hashes == want
+        for n, c, w, t in zip(names, counts, g[tag + "_counts"].tolist(), has_tie):
+            assert c == w or t, (n, c, w)
     feat, label, pad = O.synth_batch(2, 200, 80, [200, 150], seed=6)
     m.eval()
     with torch.no_grad():
@@ -505,11 +520,72 @@ def test_train_step_graph_equals_eager():
         np.random.seed(11)
         for i in range(6):
             ts.load_batch(hf, hl, hp, [256, 200])
-            ts.run()
-            if i == 0 and not use_graph:
-                ts.run(); ts.run()  # the graph path runs 2 eager warm-up steps on the first batch before capturing
+            ts.run()  # (the graph path's eager warm-up steps leave no trace: state is snapshotted and restored)
             out.append(ts.read_loss())
         losses[use_graph] = out
     assert all(np.isfinite(losses[True])) and all(np.isfinite(losses[False]))
     # same sequence of (batch, mask) pairs -> same trajectory up to fp32 atomic-add ordering
     np.testing.assert_allclose(losses[True], losses[False], rtol=2e-2)
+
+
+def test_train_step_gradient_accumulation():
+    """runner.py:370-371 / :396-399: ``accum`` micro-batches per optimizer step, loss / accum.  (1) Two copies of the
+    same micro-batch (same span mask, dropout 0) accumulate to exactly the single-batch gradient, so parameters and
+    loss after the step match the accum = 1 run; (2) the graph-captured accumulating step (two graphs) follows the
+    eager one over different micro-batches; (3) capturing leaves parameters, Adam state and the NumPy stream
+    untouched."""
+    from speech_ssl_compression_b200.trainer import TrainStep
+    from speech_ssl_compression_b200.upstream.melhubert.pretrain_expert import MelHuBERTPretrainer
+
+    cfg = base_cfg(20, 2)
+    B, T, D = 2, 256, 80
+    batches = []
+    for seed, lens in ((8, [256, 200]), (9, [256, 131])):
+        f, l, p = O.synth_batch(B, T, D, lens, seed=seed)
+        batches.append((f.pin_memory(), l.pin_memory(), p.pin_memory(), lens))
+
+    def fresh(accum, use_graph):
+        torch.manual_seed(5)
+        ex = MelHuBERTPretrainer({"melhubert": dict(cfg)}, None, DEV, False).to(DEV).train()
+        return TrainStep(ex, B, T, D, lr=1e-3, max_norm=10.0, use_graph=use_graph, accum=accum)
+
+    # (1)
+    one, two = fresh(1, False), fresh(2, False)
+    np.random.seed(3)
+    one.load_batch(*batches[0])
+    assert one.run() is True
+    for i in range(2):
+        np.random.seed(3)
+        two.load_batch(*batches[0])
+        assert two.run() is (i == 1)
+    assert abs(one.read_loss() - two.read_loss()) < 1e-4
+    # the accumulated, 1/accum-scaled gradient is the single-batch gradient: compare what is LINEAR in it (the clipped
+    # global norm and Adam's first moment; the normalised update m / sqrt(v) turns fp32 summation-order noise on
+    # near-zero gradients, e.g. the key biases, into sign flips)
+    assert abs(two.opt.grad_norm(0.5) - one.opt.grad_norm(1.0)) < 1e-4 * one.opt.grad_norm(1.0)
+    assert rel(two.opt.exp_avg, one.opt.exp_avg) < 1e-4
+    assert rel(two.flat.flat_param, one.flat.flat_param) < 1e-2
+    assert float(two.flat.flat_grad.abs().max()) == 0.0 and float(two.loss_acc) == 0.0
+    assert int(two.opt.step_count) == 1
+    # (2) + (3)
+    traj = {}
+    for use_graph in (False, True):
+        ts = fresh(2, use_graph)
+        np.random.seed(11)
+        if use_graph:
+            ts.load_batch(*batches[0])
+            p0, rng0 = ts.flat.flat_param.clone(), np.random.get_state()[1].copy()
+            np.random.seed(11)
+            ts.capture()
+            assert torch.equal(p0, ts.flat.flat_param) and int(ts.opt.step_count) == 0
+            assert float(ts.opt.exp_avg.abs().max()) == 0.0 and float(ts.flat.flat_grad.abs().max()) == 0.0
+            assert len(ts.graphs) == 2
+        out = []
+        for i in range(6):
+            ts.load_batch(*batches[i % 2])
+            if ts.run():
+                out.append(ts.read_loss())
+        traj[use_graph] = out
+        assert int(ts.opt.step_count) == 3
+    assert len(traj[True]) == 3 and traj[True][2] < traj[True][0]
+    np.testing.assert_allclose(traj[True], traj[False], rtol=2e-2)

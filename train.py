@@ -30,6 +30,7 @@ def get_args(argv=None):
     ap.add_argument("--multi_gpu", action="store_true")
     ap.add_argument("--synthetic", action="store_true", help="synthetic log-mel batches instead of the csv/npy dataset")
     ap.add_argument("--max_steps", type=int, default=None, help="override runner.total_steps")
+    ap.add_argument("--no_graph", action="store_true", help="run the step eagerly instead of replaying its CUDA graph")
     args = ap.parse_args(argv)
     os.makedirs(args.expdir, exist_ok=True)
     assert args.runner_config and args.upstream_config, "Please specify .yaml config files."

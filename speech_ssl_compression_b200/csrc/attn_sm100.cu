@@ -21,11 +21,6 @@
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
 
-// MH_ATTN_V1 (build variant, A/B only): the first forward kernel and its keep-bit layout
-#ifndef MH_ATTN_V1
-#define MH_ATTN_V1 0
-#endif
-
 namespace mh {
 extern long long g_launches;
 int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
@@ -46,7 +41,7 @@ struct AttnParams {
   float scale_log2;     // (1/sqrt(64)) * log2(e)
   DropCfg drop;
   uint32_t* keep;       // optional [B, H, keep_words, T]: dropout keep bits for the backward (word w of a query row = keys
-  int keep_words;       //   32 w .. 32 w + 31, bit order keep_bit_pos()); query-minor so that a warp (32 consecutive query rows) writes / reads one line
+  int keep_words;       //   32 w .. 32 w + 31, bit order keep_bit_pos2()); query-minor so that a warp (32 consecutive query rows) writes / reads one line
 };
 
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
@@ -56,19 +51,6 @@ __device__ __forceinline__ uint32_t swz(int r, int ch) { return r * 128 + ((ch ^
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-
-// Attention-probability dropout without predicates (the forward's softmax loop is instruction-bound).  The 128 Philox
-// bits of a group of 8 keys are eight 16-bit lanes; the low 15 bits of lane e are compared with thr15 = round(p 2^15):
-//   y = (w & 0x7fff7fff) + (0x8000 - thr15) * 0x00010001   ->  bit 15 / 31 of y = keep flag of the low / high lane.
-// prmt with sign replication turns the two flags into the 0xffff masks of the packed bf16 pair (1 instruction), and
-// the four words' flags are OR-ed, shifted by their word index, into one keep word per 32 keys:
-//   key e = 8 g + 2 j + h of a 32-key chunk  ->  bit 15 + 16 h - j - 4 g.
-__device__ __forceinline__ uint32_t sign_mask2(uint32_t y) {
-  uint32_t m;
-  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"(y));
-  return m;
-}
-__host__ __device__ constexpr int keep_bit_pos(int e) { return 15 + 16 * (e & 1) - ((e & 7) >> 1) - 4 * (e >> 3); }
 
 // rare path of the forward softmax (lazy rescaling): kept out of line so the hot loop stays small
 __device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
@@ -82,279 +64,6 @@ __device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
     tmem_st32(tmem_o_lane + c * 32, rr);
   }
   tmem_st_wait();
-}
-
-// Forward key-block size.  64 keys per block: S needs 64 TMEM columns (+ 64 for O = one 128-column allocation)
-// and the CTA 64 KB of shared memory, so THREE independent CTAs share an SM.  Softmax warps of one CTA move in
-// lockstep (they wait on the same MMA barriers); only warps of different CTAs overlap each other's stalls.
-#ifndef MH_FWD_BKV
-#define MH_FWD_BKV 64
-#endif
-constexpr int FBKV = MH_FWD_BKV;
-constexpr int FKV_TILE = FBKV * 128;            // one K or V block: FBKV rows x 128 B
-constexpr int FP_BYTES = BQ * FBKV * 2;         // bf16 P tile
-constexpr int FWD_SMEM = TILE_BYTES + 4 * FKV_TILE + FP_BYTES + 128;
-constexpr int FWD_CTAS_PER_SM = FBKV == 64 ? 3 : 2;
-constexpr int FWD_TMEM_COLS = FBKV == 64 ? 128 : 256;
-
-__global__ void __launch_bounds__(192, FWD_CTAS_PER_SM)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV,
-                const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
-  pdl_prologue();
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs a 1024-byte aligned base
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
-  uint8_t* sV = sK + 2 * FKV_TILE;     // 2 stages
-  uint8_t* sP = sV + 2 * FKV_TILE;     // one 128B-swizzle atom per 64 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FP_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * BQ;
-  const int kv_len = min(p.kv_len ? p.kv_len[b] : p.T, p.T);
-  int kv_end = kv_len;
-  if (p.causal) kv_end = min(kv_end, q0 + BQ);
-  const int n_kv = (kv_end + FBKV - 1) / FBKV;
-
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tm);
-    tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tm_out);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 5) { tmem_alloc(tmem_slot, FWD_TMEM_COLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;         // FBKV columns
-  const uint32_t tmem_o = tmem_base + FBKV;  // 64 columns
-
-  if (warp == 4) {
-    if (elect_one()) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tm, q_full, h * HD, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * FKV_TILE);
-        tma_load_3d(sK + st * FKV_TILE, &tmKV, &kv_full[st], p.E + h * HD, j * FBKV, b);
-        tma_load_3d(sV + st * FKV_TILE, &tmKV, &kv_full[st], 2 * p.E + h * HD, j * FBKV, b);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    if (elect_one()) {
-      const uint32_t idesc_s = make_idesc_bf16(BQ, FBKV, false, false);
-      const uint32_t idesc_o = make_idesc_bf16(BQ, HD, false, true);
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t a = smem_u32(sQ), bk = smem_u32(sK + st * FKV_TILE);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_s, make_sdesc(a + k * 32, 0, 1024), make_sdesc(bk + k * 32, 0, 1024), idesc_s, k > 0);
-        umma_commit(s_full);
-      };
-      if (n_kv > 0) issue_s(0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);  // P_j in smem, S_j / O_{j-1} consumed
-        tc_fence_after();
-        const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + st * FKV_TILE);
-#pragma unroll
-        for (int k = 0; k < FBKV / 16; ++k)
-          umma_bf16(tmem_o, make_sdesc(ap + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024),
-                    make_sdesc(bv + k * 2048, FKV_TILE, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&kv_empty[st]);
-        umma_commit(o_full);
-        if (j + 1 < n_kv) issue_s(j + 1);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ softmax warps
-    // Thread t owns query row t.  O accumulates in TMEM across key blocks; the running maximum is only
-    // raised when a block exceeds it by more than 2^8 (lazy rescaling: probabilities stay <= 256, the
-    // final division by the row sum is exact either way), so the O read-modify-write is a rare path.
-    const int r = threadIdx.x;  // query row inside the tile == TMEM lane
-    const int q = q0 + r;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const uint64_t row_id = (static_cast<uint64_t>(b) * p.H + h) * p.T + q;
-    const uint64_t groups_per_row = (p.T + 7) >> 3;
-    const float sc = p.scale_log2;
-    const bool use_drop = p.drop.thresh != 0;
-    const DropState ds(p.drop);
-    const uint32_t drop_add = (0x8000u - ((p.drop.thresh + 1u) >> 1)) * 0x00010001u;  // see sign_mask2
-    // the dropout keep-scale 1/(1-p) is folded into the exponent: probabilities (and the running row sum)
-    // carry the constant factor, which the final normalisation and the saved log-sum-exp divide out again
-    const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int k0 = j * FBKV;
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      int lim = kv_len - k0;                       // keys [0, lim) of this block are visible
-      if (p.causal) lim = min(lim, q - k0 + 1);
-      // ---- reference maximum.  TMEM -> register bandwidth is the scarce resource of this kernel, so the
-      // score tile is read ONCE per block where possible: only the first block runs a separate max pass; later
-      // blocks exponentiate against the running reference m_run and track their own maximum on the fly.
-      // Any reference gives the exact softmax as long as nothing overflows (bf16 P and fp32 sums share the
-      // fp32 exponent range), so the reference is only raised -- O and l rescaled, the block redone -- when
-      // a block exceeds it by more than 2^64 (practically never; the path exists for correctness).
-      if (j == 0) {
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < FBKV / 32; ++c) {
-          uint32_t rr[32];
-          tmem_ld32(tmem_s + lane_off + c * 32, rr);
-          tmem_ld_wait();
-          const int rem32 = lim - c * 32;
-          if (rem32 >= 32) {
-            float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                m4[u] = fmaxf(m4[u], fmaxf(__uint_as_float(rr[i + 2 * u]), __uint_as_float(rr[i + 2 * u + 1])));
-            }
-            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < rem32) mx = fmaxf(mx, __uint_as_float(rr[i]));
-          }
-        }
-        m_run = mx * sc;
-      }
-      // ---- probabilities, row sum, dropout, bf16 P into swizzled smem
-      float l4[4];
-      // keep bits of this row's keys (saved for the backward: 1 bit per score instead of a second Philox pass)
-      uint32_t* const keep_row = (use_drop && p.keep != nullptr && q < p.T)
-                                     ? p.keep + ((static_cast<long long>(b) * p.H + h) * p.keep_words + (k0 >> 5)) * p.T + q
-                                     : nullptr;
-      const uint64_t drop_base = row_id * groups_per_row + static_cast<uint64_t>(k0 >> 3);
-#pragma unroll 1
-      for (int attempt = 0; attempt < 2; ++attempt) {
-        const float m_off = (m_run == -INFINITY ? 0.f : m_run) - lg_scale;
-        float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        l4[0] = l4[1] = l4[2] = l4[3] = 0.f;
-        // one 32-key chunk per trip (4 groups of 8 unrolled inside): measured best trade between instruction
-        // level parallelism and code size (the fully unrolled 128-key body was fetch-bound, 25 % slower)
-#pragma unroll 1
-        for (int c = 0; c < FBKV / 32; ++c) {
-          uint32_t rr[32];
-          tmem_ld32(tmem_s + lane_off + c * 32, rr);
-          tmem_ld_wait();
-          uint32_t kw = 0u;  // keep bits of the 32 keys of this chunk
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int rem = lim - (c * 32 + g * 8);  // visible keys left in this group (only the last block has < 8)
-            if (rem < 8) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (i >= rem) rr[g * 8 + i] = 0xff800000u;  // -inf: probability 0, ignored by the maximum
-            }
-            float pv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(rr[g * 8 + i]), sc, -m_off));
-            b4[g] = fmaxf(b4[g], fmaxf(fmaxf(fmaxf(__uint_as_float(rr[g * 8]), __uint_as_float(rr[g * 8 + 1])),
-                                             fmaxf(__uint_as_float(rr[g * 8 + 2]), __uint_as_float(rr[g * 8 + 3]))),
-                                       fmaxf(fmaxf(__uint_as_float(rr[g * 8 + 4]), __uint_as_float(rr[g * 8 + 5])),
-                                             fmaxf(__uint_as_float(rr[g * 8 + 6]), __uint_as_float(rr[g * 8 + 7])))));
-            // pairwise tree + four accumulators: no long dependent FADD chain
-            l4[g] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
-            uint4 pw = f32_to_bf16x8(pv);
-            if (use_drop) {
-              const uint4 bits = ds.bits(p.drop, drop_base + (c * 4 + g));
-              const uint32_t y0 = (bits.x & 0x7fff7fffu) + drop_add, y1 = (bits.y & 0x7fff7fffu) + drop_add;
-              const uint32_t y2 = (bits.z & 0x7fff7fffu) + drop_add, y3 = (bits.w & 0x7fff7fffu) + drop_add;
-              pw.x &= sign_mask2(y0); pw.y &= sign_mask2(y1); pw.z &= sign_mask2(y2); pw.w &= sign_mask2(y3);
-              const uint32_t t = (y0 & 0x80008000u) | ((y1 & 0x80008000u) >> 1) | ((y2 & 0x80008000u) >> 2) |
-                                 ((y3 & 0x80008000u) >> 3);
-              kw |= t >> (4 * g);
-            }
-            const int kc = c * 32 + g * 8;  // key column inside the block
-            uint8_t* dst = sP + (kc >> 6) * TILE_BYTES + swz(r, (kc & 63) >> 3);
-            *reinterpret_cast<uint4*>(dst) = pw;
-          }
-          if (keep_row != nullptr) keep_row[static_cast<long long>(c) * p.T] = kw;
-        }
-        const float m_blk = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3])) * sc;
-        const bool need = m_blk > m_run + 64.0f;  // (false for m_blk = -inf and for attempt 1)
-        if (!__any_sync(0xffffffffu, need)) break;
-        // rare: raise the reference of the offending rows, rescale their O / l, redo the block
-        const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;  // m_run = -inf -> 0
-        if (j > 0) {
-          mbar_wait(o_full, (j - 1) & 1);  // PV_{j-1} must have landed before O is touched
-          tc_fence_after();
-          rescale_o_rows(tmem_o + lane_off, alpha);
-        }
-        l_run *= alpha;
-        if (need) m_run = m_blk;
-      }
-      l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    if (n_kv > 0) {
-      mbar_wait(o_full, (n_kv - 1) & 1);
-      tc_fence_after();
-    }
-    // with the keep-scale s folded in: l_run = s * sum(e), O_tmem = s * sum(keep e v)  ->  out = O_tmem * s / l_run
-    const float inv = l_run > 0.f ? (use_drop ? p.drop.scale : 1.f) / l_run : 0.f;
-    // The bf16 output tile goes through the (now idle) Q buffer and leaves as ONE TMA tile store: per-thread row
-    // stores are 16 bytes per lane into 32 different lines per instruction, which kept the LSU busy for thousands
-    // of cycles per CTA (rows past the sequence end are clipped by the tensor map).
-    const uint32_t o_row = smem_u32(sQ) + r * 128;
-#pragma unroll
-    for (int c = 0; c < HD / 32; ++c) {
-      uint32_t rr[32];
-      if (n_kv > 0) {
-        tmem_ld32(tmem_o + lane_off + c * 32, rr);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rr[i] = 0u;
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[g * 8 + i]) * inv;
-        sts128(o_row + (((c * 4 + g) ^ (r & 7)) << 4), f32_to_bf16x8(v));
-      }
-    }
-    fence_proxy_async_smem();
-    bar_sync(1, 128);
-    if (threadIdx.x == 0) {
-      tma_store_3d(&tm_out, sQ, h * HD, q0, b);
-      bulk_commit();
-      bulk_wait_read0();  // the CTA may exit (and its shared memory be reused) once the tile has been read
-    }
-    if (q < p.T)
-      p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l_run > 0.f ? m_run + log2f(l_run) - lg_scale : INFINITY;
-    tc_fence_before();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, FWD_TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------- forward, version 2
@@ -398,29 +107,6 @@ struct F2Cfg {
   static constexpr int kOCol = 2 * BKV;                      // first TMEM column of O
 };
 
-__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -447,21 +133,6 @@ __device__ __forceinline__ void keep_pair_masks(uint32_t kw, uint32_t (&m)[16]) 
   }
 }
 
-struct AttnDrop2 {
-  uint32_t tmask[12];  // plane k: all-ones when bit k of the 12-bit threshold is set
-  float keep_scale;    // 4096 / (4096 - thr12)
-  float lg_scale;      // log2(keep_scale)
-};
-__host__ inline AttnDrop2 make_drop2(float p) {
-  AttnDrop2 d;
-  uint32_t thr = p > 0.f ? static_cast<uint32_t>(p * 4096.0f + 0.5f) : 0u;
-  if (thr > 4095u) thr = 4095u;
-  for (int k = 0; k < 12; ++k) d.tmask[k] = ((thr >> k) & 1u) ? 0xffffffffu : 0u;
-  d.keep_scale = 4096.0f / static_cast<float>(4096u - thr);
-  d.lg_scale = log2f(d.keep_scale);
-  return d;
-}
-
 #ifndef MH_F2_TRACE
 #define MH_F2_TRACE 0  // debug build: clock64 stamps of one CTA per SM-slot sample (mh_attn_trace_read)
 #endif
@@ -472,10 +143,33 @@ __device__ long long g_f2_trace[8][64][8];
 #define F2_STAMP(slot, blk, what) do { } while (0)
 #endif
 
+// row maximum of the visible keys [0, lim) of one score block (rare path: block 0 of a row, or a block whose sum left
+// the safe range of the running reference) -- out of line so that the hot loop's register budget ignores it
+template <int BKV>
+__device__ __noinline__ float f2_block_max(uint32_t ts, int lim) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+  for (int c = 0; c < BKV / 32; ++c) {
+    uint32_t s[32];
+    tmem_ld32(ts + c * 32, s);
+    tmem_ld_wait();
+    if (lim < (c + 1) * 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i >= lim) s[i] = 0xff800000u;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = fmax3(m4[u], __uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1]));
+  }
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
 template <int BKV>
 __global__ void __launch_bounds__(192, F2Cfg<BKV>::kCtasPerSm)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmKV,
-                 const __grid_constant__ CUtensorMap tm_out, const AttnParams p, const AttnDrop2 d2) {
+                 const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
   using Cfg = F2Cfg<BKV>;
   constexpr int NST = Cfg::kStages, KV_TILE = Cfg::kTile, NCH = BKV / 32;
   pdl_prologue();
@@ -594,131 +288,95 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__
     const float sc = p.scale_log2;
     const bool use_drop = p.drop.thresh != 0;
     const DropState ds(p.drop);
-    const float lg_scale = use_drop ? d2.lg_scale : 0.f;
+    const float lg_scale = use_drop ? log2f(p.drop.scale) : 0.f;
     const uint64_t row_id = (static_cast<uint64_t>(b) * p.H + h) * p.T + q;
     const uint64_t chunks_per_row = (p.T + 31) >> 5;
     uint32_t* keep_ptr = (use_drop && p.keep != nullptr && q < p.T)
                              ? p.keep + (static_cast<long long>(b) * p.H + h) * p.keep_words * p.T + q
                              : nullptr;
-    uint64_t drop_ctr = row_id * chunks_per_row * 4;  // Philox counter of (row, 32-key chunk, call t): + 4 chunk + t
+    uint64_t drop_word = row_id * chunks_per_row;  // dropout stream word of (row, 32-key chunk): + chunk
     const uint64_t sc2 = pack2f(sc, sc);
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ts = tmem_s + (j & 1) * BKV + lane_off;
       F2_STAMP(0, j, 0);
+      // Dropout keep words of this block FIRST: they do not depend on the scores, so the Philox rounds run while S_j may
+      // still be in flight, and their ~20 live registers are dead again before the score registers are loaded.
+      uint32_t ge[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) ge[c] = 0xffffffffu;
+      if (use_drop) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          ge[c] = ds.keep32(p.drop, drop_word++);  // bit-sliced dropout, mh_common.cuh (bit order: keep_bit_pos2)
+          if (keep_ptr != nullptr && !(MH_F2_KO & 4)) {
+            *keep_ptr = ge[c];
+            keep_ptr += p.T;
+          }
+        }
+      }
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       F2_STAMP(0, j, 1);
       int lim = kv_len - j * BKV;  // keys [0, lim) of this block are visible to this row
       if (p.causal) lim = min(lim, q - j * BKV + 1);
+      // reference maximum: block 0 only (out of line: one extra read of S_0); later blocks reuse it, see header
+      if (j == 0) m_run = f2_block_max<BKV>(ts, lim) * sc;
       uint32_t pk[NCH][16];  // bf16 pairs of the block's probabilities
       float l_blk;
 #pragma unroll 1
-      for (int attempt = 0; attempt < 2; ++attempt) {
-        uint32_t s[NCH][32];
-#if MH_F2_KO & 8
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(static_cast<float>((r * 7 + i * 3 + j) & 15));
-#else
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_ld32(ts + c * 32, s[c]);
-        tmem_ld_wait();
-#endif
-        if (lim < BKV) {  // last (or diagonal) block only
-#pragma unroll
-          for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= lim) s[c][i] = 0xff800000u;  // -inf: probability 0
-        }
-        if (j == 0 || attempt == 1) {
-          // reference maximum of the row: first block, or a block that left the safe range of the old reference
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 8)
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                m4[u] = fmax3(m4[u], __uint_as_float(s[c][i + 2 * u]), __uint_as_float(s[c][i + 2 * u + 1]));
-          const float m_blk = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
-          if (attempt == 1) {
-            // rare: rescale what has been accumulated against the old reference (warp-uniform branch: tcgen05.ld /
-            // st are warp-collective; rows that did not overflow keep alpha = 1)
-            const bool need = !(l_blk < 1e30f) && m_blk > m_run;
-            const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;  // m_run = -inf -> 0
-            if (j > 0) {
-              mbar_wait(o_full, (j - 1) & 1);  // P_{j-1} V_{j-1} must have landed before O is touched
-              tc_fence_after();
-              rescale_o_rows(tmem_o + lane_off, alpha);
-            }
-            l_run *= alpha;
-            if (need) m_run = m_blk;
-          } else {
-            m_run = m_blk;
-          }
-        }
+      for (int attempt = 0;; ++attempt) {
         const float m_off = (m_run == -INFINITY ? 0.f : m_run) - lg_scale;
         const uint64_t nm2 = pack2f(-m_off, -m_off);
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          uint32_t s[32];
+#if MH_F2_KO & 8
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(static_cast<float>((r * 7 + i * 3 + j) & 15));
+#else
+          tmem_ld32(ts + c * 32, s);
+          tmem_ld_wait();
+#endif
+          if (lim < (c + 1) * 32) {  // last (or diagonal) block only
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= lim) s[i] = 0xff800000u;  // -inf: probability 0
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float x0, x1;
-            unpack2f(ffma2(pack2f(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2), x0, x1);
+            unpack2f(ffma2(pack2f(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2), x0, x1);
 #if MH_F2_KO & 1
             const float e0 = x0 * x0, e1 = x1 * x1;
 #else
             const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
 #endif
             acc[i & 3] = fadd2(acc[i & 3], pack2f(e0, e1));
-            pk[c][i] = pack_bf16(e0, e1);
+            // pair i = 2 sft + u of the chunk: keep masks = replicated MSBs of bytes (1, 3) / (0, 2) of (word << sft)
+            pk[c][i] = pack_bf16(e0, e1) & ((i & 1) ? prmt_sel<0xAA88>(ge[c] << (i >> 1)) : prmt_sel<0xBB99>(ge[c] << (i >> 1)));
           }
         }
         float a0, a1;
         unpack2f(fadd2(fadd2(acc[0], acc[1]), fadd2(acc[2], acc[3])), a0, a1);
         l_blk = a0 + a1;
         // a row sum anywhere near the fp32 / bf16 overflow range means this block's scores exceed the reference by
-        // > 2^90: raise the reference and redo the block (never taken with bounded activations)
+        // > 2^90: raise the reference, rescale what has been accumulated and redo the block (never taken with bounded
+        // activations; warp-uniform branch: tcgen05.ld / st are warp-collective)
         if (attempt == 1 || !__any_sync(0xffffffffu, !(l_blk < 1e30f))) break;
+        const float m_blk = f2_block_max<BKV>(ts, lim) * sc;
+        const bool need = !(l_blk < 1e30f) && m_blk > m_run;
+        const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;  // m_run = -inf -> 0
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);  // P_{j-1} V_{j-1} must have landed before O is touched
+          tc_fence_after();
+          rescale_o_rows(tmem_o + lane_off, alpha);
+        }
+        l_run *= alpha;
+        if (need) m_run = m_blk;
       }
       l_run += l_blk;
-      F2_STAMP(0, j, 2);
-      if (use_drop) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t w[12];
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
-#if MH_F2_KO & 2
-            const uint32_t cc = static_cast<uint32_t>(drop_ctr) + t;
-            const uint4 bits = make_uint4(cc * 0x9E3779B9u, cc ^ 0x12345u, cc + 77u, ~cc);
-#else
-            const uint4 bits = ds.bits(p.drop, drop_ctr + t);
-#endif
-            w[4 * t] = bits.x; w[4 * t + 1] = bits.y; w[4 * t + 2] = bits.z; w[4 * t + 3] = bits.w;
-          }
-          drop_ctr += 4;
-          // keep iff R >= thr (R = the 12-bit number whose bit k is plane k): compare from the least significant plane up
-          uint32_t ge = 0xffffffffu;
-#pragma unroll
-          for (int k = 0; k < 12; ++k)  // ge = t ? (w & ge) : (w | ge) -- one LOP3 per plane
-            asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(w[k]), "r"(d2.tmask[k]));
-          if (keep_ptr != nullptr && !(MH_F2_KO & 4)) {
-            *keep_ptr = ge;
-            keep_ptr += p.T;
-          }
-#pragma unroll
-          for (int sft = 0; sft < 8; ++sft) {
-            const uint32_t a = ge << sft;
-            pk[c][2 * sft] &= prmt_sel<0xBB99>(a);
-            pk[c][2 * sft + 1] &= prmt_sel<0xAA88>(a);
-          }
-        }
-      }
       F2_STAMP(0, j, 3);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) tmem_st16(ts + c * 16, pk[c]);
@@ -735,7 +393,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__
       mbar_wait(q_full, 0);  // the output tile is staged in the Q buffer: its (unused) load must have landed
     }
     // with the keep-scale s folded in: l_run = s * sum(e), O_tmem = s * sum(keep e v)  ->  out = O_tmem * s / l_run
-    const float inv = l_run > 0.f ? (use_drop ? d2.keep_scale : 1.f) / l_run : 0.f;
+    const float inv = l_run > 0.f ? (use_drop ? p.drop.scale : 1.f) / l_run : 0.f;
     const uint32_t o_row = smem_u32(sQ) + r * 128;
 #pragma unroll 1
     for (int c = 0; c < HD / 32; ++c) {
@@ -806,12 +464,6 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
     }
   }
 }
-
-#if MH_ATTN_V1
-#define KEEP_POS keep_bit_pos
-#else
-#define KEEP_POS keep_bit_pos2
-#endif
 
 struct AttnBwdParams {
   const int* kv_len;
@@ -1334,14 +986,13 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   CUtensorMap tm, tmkv;
   int rc = make_tmap_3d(&tm, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, BQ);
   if (rc) return rc;
-  rc = make_tmap_3d(&tmkv, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, MH_ATTN_V1 ? FBKV : MH_F2_BKV);
+  rc = make_tmap_3d(&tmkv, qkv, 3LL * E, T, B, 3LL * E, static_cast<long long>(T) * 3 * E, HD, MH_F2_BKV);
   if (rc) return rc;
   CUtensorMap tmo;
   rc = make_tmap_3d(&tmo, out, E, T, B, E, static_cast<long long>(T) * E, HD, BQ);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    MH_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     MH_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<MH_F2_BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Cfg<MH_F2_BKV>::kSmem));
     configured = true;
   }
@@ -1352,12 +1003,8 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   p.drop = make_drop(p_drop, seed, site);
   p.keep = reinterpret_cast<uint32_t*>(keep_bits);
   p.keep_words = ((T + 127) / 128) * 4;
-#if MH_ATTN_V1
-  MH_CUDA(launch_pdl(attn_fwd_kernel, dim3((T + BQ - 1) / BQ, heads, B), dim3(192), FWD_SMEM, st, tm, tmkv, tmo, p));
-#else
   MH_CUDA(launch_pdl(attn_fwd2_kernel<MH_F2_BKV>, dim3((T + BQ - 1) / BQ, heads, B), dim3(192), F2Cfg<MH_F2_BKV>::kSmem, st,
-                     tm, tmkv, tmo, p, make_drop2(p_drop)));
-#endif
+                     tm, tmkv, tmo, p));
   ++g_launches;
   return 0;
 }
@@ -1410,11 +1057,7 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   p.drop = make_drop(p_drop, seed, site);
   p.keep = reinterpret_cast<const uint32_t*>(keep_bits);
   p.keep_words = ((T + 127) / 128) * 4;
-#if MH_ATTN_V1
   p.keep_scale = p.drop.scale;
-#else
-  p.keep_scale = make_drop2(p_drop).keep_scale;
-#endif
   {
     const long long items = static_cast<long long>((T + BKV - 1) / BKV) * heads * B;
     MH_CHECK(items < (1LL << 31), "attn_bwd: too many work items");

@@ -170,14 +170,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   // sub-chunk loop stays rolled (the unrolled 64-column body was ~30 KB of SASS per kernel and fetch-bound
   // like the attention loops), so the held values live in two explicitly named register sets.
   uint4 held0[4], held1[4];
-  // dropout stream position of this thread's row (element (row, col) lives in group row * N/8 + col/8)
-  const uint64_t drop_base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 3) + static_cast<uint64_t>(n0 >> 3);
+  // dropout stream position of this thread's row (element (row, col) lives in word row * N/32 + col/32, bit col % 32)
+  const uint64_t drop_base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 5) + static_cast<uint64_t>(n0 >> 5);
   const DropState dstate(p.drop);  // (device step counter: one L1-resident load per tile)
   if (active) {
     auto sub_chunk = [&](int s) {
       const int col_in_tile = e.grp * CG + s * 32;
+      // the 32 keep decisions of this thread's 32 columns: generated while the accumulator load is in flight
+      constexpr bool HAS_DROP = EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU;
       uint32_t r[32];
       tmem_ld32(tmem_acc + e.lane_off + col_in_tile, r);
+      uint32_t kw = 0xffffffffu;
+      if (HAS_DROP && p.drop.thresh != 0) kw = dstate.keep32(p.drop, drop_base + (col_in_tile >> 5));
       tmem_ld_wait();
       uint4 o4[4];
 #pragma unroll
@@ -203,17 +207,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           const uint4 pre = f32_to_bf16x8(v);
           if (p.has_aux_out) *reinterpret_cast<uint4*>(slot) = pre;
           bf16x8_to_f32(pre, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+          gelu_erf8(v);
         }
         if (EPI == MH_EPI_DGELU) {
           float pre[8];
           bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), pre);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(pre[j]);
+          gelu_erf_grad_mul8(v, pre);
         }
-        if (EPI == MH_EPI_GELU || EPI == MH_EPI_RES || EPI == MH_EPI_DGELU) {
-          if (p.drop.thresh != 0) dstate.apply8(p.drop, drop_base + ((col_in_tile + q * 8) >> 3), v);
+        if (HAS_DROP) {
+          if (p.drop.thresh != 0) DropState::apply8(p.drop, kw >> (8 * q), v);
         }
         if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
           float a[8];
@@ -872,6 +874,7 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   d.has_aux_out = a->aux_out != nullptr;
   d.mask = a->mask;
   d.drop = make_drop(a->p_drop, a->seed, a->site);
+  MH_CHECK(d.drop.thresh == 0 || a->N % 32 == 0, "gemm: a dropout epilogue needs N %% 32 == 0 (one dropout stream word = 32 columns), got N=%d", a->N);
   d.split_k = splits;
   const int tiles = tiles_m * num_n * splits;
   if (pair) return dispatch_epi_pair(a, t, d, 2 * (tiles < units ? tiles : units), st);

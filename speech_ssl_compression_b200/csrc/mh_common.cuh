@@ -61,23 +61,32 @@ inline cudaError_t launch_pdl_f(int family, void (*kernel)(KArgs...), dim3 grid,
 #define launch_pdl(...) launch_pdl_f(MH_PDL_FAMILY, __VA_ARGS__)
 
 // ---- Philox4x32-7 (Salmon et al., SC'11: 7 rounds is the smallest crush-resistant variant) ----
-// Dropout over a logical element stream.  One Philox call covers 8 consecutive elements (eight 16-bit lanes, low
-// half of each word first); element e is kept iff lane(e) >= thresh, thresh = round(p * 65536).  The forward and
-// the backward regenerate identical decisions from (seed, device step counter, site, element / 8):
+// Bit-sliced dropout over a logical element stream.  The stream is cut into WORDS of 32 consecutive elements; one
+// thread produces the 32 keep decisions of a word at once:
+//   * every element gets a 12-bit random number R, stored bit-sliced: plane k is a 32-bit word whose bit i is bit k of
+//     element i's number.  Planes 4..11 (the eight most significant bits) are the 8 output words of two Philox4x32-7
+//     calls; planes 0..3 only matter to the 1 element in 256 whose upper bits equal the threshold's, and are lane
+//     rotations of the upper planes -- for such an element its own upper bits are fixed, so its low bits are the
+//     (independent, uniform) upper bits of the elements 11 and 19 positions away: unbiased at 3 instead of 7
+//     instructions per plane;
+//   * element i is kept iff R_i >= thr, thr = round(p * 4096): a 12-step LOP3 chain, one instruction per plane for all
+//     32 decisions (tmask[k] = all-ones when bit k of thr is set); survivors are scaled by 4096 / (4096 - thr).
+//   p is therefore quantised to 1/4096 (0.1 -> 410/4096 = 0.100098).
+// 2 x (14 IMAD.WIDE + 14 LOP3) + 12 + 12 instructions for 32 decisions = 2.5 per element; the first scheme (one call
+// per 8 elements, 16-bit lane compares) cost 8.5 per element and was 35 % of the instruction-bound GELU / dropout
+// GEMM epilogues.  The forward and the backward regenerate identical decisions from (seed, device step counter,
+// site, word index):
 //   key     = seed                      -> the 7 round-key pairs are computed ON THE HOST (make_drop) and travel in
-//                                          the kernel parameters: they are constant-bank operands of the LOP3s, no
-//                                          registers and no per-call key schedule
-//   counter = (group_lo, group_hi ^ step_lo, site, 0x9E3779B9 ^ step_hi); `step` is the optional device counter
-//             (CUDA-graph replays advance it), read once per thread (DropState).
-// A call is 14 IMAD.WIDE + 14 LOP3 (+1) for 8 decisions.  (The first version folded the device counter into the
-// KEY: every call re-derived the key schedule and re-read the counter, ~100 instructions per 8 elements, 45 % of
-// the instruction-bound GELU / dropout GEMM epilogues and a third of the LayerNorm backward.)
+//                                          the kernel parameters: constant-bank operands of the LOP3s
+//   counter = (c_lo, c_hi ^ step_lo, site, 0x9E3779B9 ^ step_hi), c = 2 * word + call; `step` is the optional device
+//             counter (CUDA-graph replays advance it), read once per thread (DropState).
 struct DropCfg {
   uint32_t ka[7], kb[7];             // Philox round keys: ka[r] = seed_lo + r * 0x9E3779B9, kb[r] = seed_hi + r * 0xBB67AE85
   const unsigned long long* offset;  // optional device step counter (CUDA-graph replays)
   uint32_t site;    // unique per dropout site (layer * 8 + site id)
-  uint32_t thresh;  // 0 => dropout disabled
-  float scale;      // 1 / (1 - p)
+  uint32_t thresh;  // thr = round(p * 4096); 0 => dropout disabled
+  float scale;      // 4096 / (4096 - thr)
+  uint32_t tmask[12];  // plane k: all-ones when bit k of thr is set
 };
 const unsigned long long* dropout_offset_ptr();
 __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
@@ -86,9 +95,11 @@ __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
   for (int r = 0; r < 7; ++r) { d.ka[r] = a; d.kb[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
   d.offset = dropout_offset_ptr();
   d.site = site;
-  d.thresh = p > 0.f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u;
-  if (d.thresh > 65535u) d.thresh = 65535u;
-  d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  d.thresh = p > 0.f ? static_cast<uint32_t>(p * 4096.0f + 0.5f) : 0u;
+  if (p > 0.f && d.thresh == 0u) d.thresh = 1u;
+  if (d.thresh > 4095u) d.thresh = 4095u;
+  d.scale = 4096.0f / static_cast<float>(4096u - d.thresh);
+  for (int k = 0; k < 12; ++k) d.tmask[k] = ((d.thresh >> k) & 1u) ? 0xffffffffu : 0u;
   return d;
 }
 
@@ -103,9 +114,9 @@ struct DropState {
     c1 = static_cast<uint32_t>(o);
     c3 = 0x9E3779B9u ^ static_cast<uint32_t>(o >> 32);
   }
-  // the 128 random bits of `group` (lane j of the group = 16-bit field j, low half first)
-  __device__ __forceinline__ uint4 bits(const DropCfg& d, uint64_t group) const {
-    uint32_t x0 = static_cast<uint32_t>(group), x1 = static_cast<uint32_t>(group >> 32) ^ c1, x2 = d.site, x3 = c3;
+  // one Philox4x32-7 block
+  __device__ __forceinline__ uint4 bits(const DropCfg& d, uint64_t ctr) const {
+    uint32_t x0 = static_cast<uint32_t>(ctr), x1 = static_cast<uint32_t>(ctr >> 32) ^ c1, x2 = d.site, x3 = c3;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
       const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * x0;
@@ -116,30 +127,41 @@ struct DropState {
     }
     return make_uint4(x0, x1, x2, x3);
   }
-  // v[j] = keep_j ? v[j] * scale : 0 for the 8 elements of `group`, without materialising the bit mask:
-  // the high field is compared in place (word >= thresh << 16), the low one after a 16-bit shift.
-  __device__ __forceinline__ void apply8(const DropCfg& d, uint64_t group, float (&v)[8]) const {
-    const uint4 r = bits(d, group);
-    const uint32_t t = d.thresh << 16;
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  // the 32 keep decisions of stream word `word`: bit i = element 32 word + i is kept
+  __device__ __forceinline__ uint32_t keep32(const DropCfg& d, uint64_t word) const {
+    uint32_t w[12];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = (w[i] << 16) >= t ? v[2 * i] * d.scale : 0.f;
-      v[2 * i + 1] = w[i] >= t ? v[2 * i + 1] * d.scale : 0.f;
+    for (int t = 0; t < 2; ++t) {
+      const uint4 b = bits(d, 2 * word + t);
+      w[4 + 4 * t] = b.x; w[5 + 4 * t] = b.y; w[6 + 4 * t] = b.z; w[7 + 4 * t] = b.w;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = __funnelshift_l(w[4 + k], w[4 + k], 11) ^ __funnelshift_l(w[8 + k], w[8 + k], 19);
+    uint32_t ge = 0xffffffffu;  // R >= thr, compared from the least significant plane up
+#pragma unroll
+    for (int k = 0; k < 12; ++k)  // ge = t ? (w & ge) : (w | ge) -- one LOP3 per plane
+      asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(w[k]), "r"(d.tmask[k]));
+    return ge;
   }
-  // keep-mask bits (bit j = element j kept) of the 8 elements of `group`
-  __device__ __forceinline__ uint32_t keep8(const DropCfg& d, uint64_t group) const {
-    const uint4 r = bits(d, group);
-    const uint32_t t = d.thresh << 16;
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    uint32_t m = 0;
+  // v[j] = keep_j ? v[j] * scale : 0 for 8 consecutive elements whose keep bits are bits 0..7 of `kb`
+  __device__ __forceinline__ static void apply8(const DropCfg& d, uint32_t kb, float (&v)[8]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      m |= ((w[i] << 16) >= t ? 1u : 0u) << (2 * i);
-      m |= (w[i] >= t ? 1u : 0u) << (2 * i + 1);
+    for (int j = 0; j < 8; ++j) v[j] = (kb & (1u << j)) ? v[j] * d.scale : 0.f;
+  }
+  // Warp-cooperative form for kernels in which lane l owns the 8-element chunks c = l + 32 i (i < NCH) of a row of
+  // `nchunks` chunks (nchunks % 4 == 0, nchunks <= 128): lanes 0 .. nchunks / 4 - 1 generate one word each, every lane
+  // then fetches the byte of each of its chunks.  Must be called by all 32 lanes.  `first_word` = word index of the
+  // row's first element.
+  template <int NCH>
+  __device__ __forceinline__ void keep_bytes_row(const DropCfg& d, uint64_t first_word, int nchunks, int lane,
+                                                 uint32_t (&kb)[NCH]) const {
+    uint32_t w = 0xffffffffu;
+    if (lane < (nchunks >> 2)) w = keep32(d, first_word + lane);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      kb[i] = (__shfl_sync(0xffffffffu, w, (c >> 2) & 31) >> (8 * (c & 3))) & 0xffu;
     }
-    return m;
   }
 };
 

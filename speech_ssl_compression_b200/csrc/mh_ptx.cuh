@@ -256,6 +256,30 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// ------------------------------------------------------------------ packed fp32 (two lanes per instruction: FFMA2 / FADD2 / FMUL2)
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -268,5 +292,48 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+
+// ------------------------------------------------------------------ erf-GELU on packed fp32 pairs
+// Same fit as gelu_erf / gelu_erf_grad (mh_common.cuh: 0.5 erfc(a / sqrt 2) = 2^(-a p(a) - 1), quartic p), evaluated
+// on two values per FFMA2.  Written in na = -|x| (one OR with the sign bit per value), so neither fabs nor negations
+// are needed: p(a) = c0 - c1 na + c2 na^2 - c3 na^3 + c4 na^4, exponent = P na - 1, gelu = max(x, 0) + na e.
+// 6 instructions per value (scalar: 9); the GELU / dGELU GEMM epilogues are issue-bound, see gemm_sm100.cu.
+__device__ __forceinline__ uint64_t erfc_half_scaled2(uint64_t na2) {  // (0.5 erfc(|x| / sqrt 2)) x 2, argument -|x|
+  uint64_t p = pack2f(4.88221852e-04f, 4.88221852e-04f);
+  p = ffma2(p, na2, pack2f(7.19561887e-03f, 7.19561887e-03f));
+  p = ffma2(p, na2, pack2f(5.21302448e-02f, 5.21302448e-02f));
+  p = ffma2(p, na2, pack2f(-4.59620056e-01f, -4.59620056e-01f));
+  p = ffma2(p, na2, pack2f(1.15099005e+00f, 1.15099005e+00f));
+  float t0, t1;
+  unpack2f(ffma2(p, na2, pack2f(-1.0f, -1.0f)), t0, t1);
+  return pack2f(ex2_approx(t0), ex2_approx(t1));
+}
+__device__ __forceinline__ void gelu_erf8(float (&v)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float x0 = v[2 * k], x1 = v[2 * k + 1];
+    const uint64_t na2 = pack2f(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));
+    unpack2f(ffma2(na2, erfc_half_scaled2(na2), pack2f(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), v[2 * k], v[2 * k + 1]);
+  }
+}
+// v[j] *= d gelu / dx at pre[j]:  Phi(x) + x phi(x),  Phi = 0.5 + copysign(0.5 - e, x),  phi = 0.39894228 2^(-0.72134752 x^2)
+__device__ __forceinline__ void gelu_erf_grad_mul8(float (&v)[8], const float (&pre)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float x0 = pre[2 * k], x1 = pre[2 * k + 1];
+    const uint64_t x2 = pack2f(x0, x1);
+    const uint64_t na2 = pack2f(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));
+    float t0, t1;
+    unpack2f(ffma2(erfc_half_scaled2(na2), pack2f(-1.0f, -1.0f), pack2f(0.5f, 0.5f)), t0, t1);  // 0.5 - e >= 0
+    const uint64_t ts = pack2f(__uint_as_float(__float_as_uint(t0) | (__float_as_uint(x0) & 0x80000000u)),
+                               __uint_as_float(__float_as_uint(t1) | (__float_as_uint(x1) & 0x80000000u)));
+    float a0, a1;
+    unpack2f(fmul2(fmul2(x2, x2), pack2f(-0.72134752044f, -0.72134752044f)), a0, a1);
+    const uint64_t pdf = pack2f(ex2_approx(a0), ex2_approx(a1));
+    const uint64_t g = ffma2(fmul2(x2, pack2f(0.39894228040143268f, 0.39894228040143268f)), pdf, fadd2(ts, pack2f(0.5f, 0.5f)));
+    unpack2f(fmul2(pack2f(v[2 * k], v[2 * k + 1]), g), v[2 * k], v[2 * k + 1]);
+  }
+}
 
 }  // namespace mh

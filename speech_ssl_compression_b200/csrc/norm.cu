@@ -94,6 +94,8 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
     }
     __nv_bfloat16* yr = y + static_cast<long long>(row) * cols + lane * 8;
     const float nmr = -mean * rstd;
+    uint32_t kb[NCH];  // keep bits of this lane's chunks (bit-sliced dropout: 32 decisions per generated word)
+    if (drop.thresh != 0) dstate.keep_bytes_row<NCH>(drop, static_cast<uint64_t>(row) * (nchunks >> 2), nchunks, lane, kb);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       if (EXACT || lane + 32 * i < nchunks) {
@@ -107,9 +109,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[i][j], rstd, nmr), g[j], b[j]);
-        if (drop.thresh != 0) {
-          dstate.apply8(drop, static_cast<uint64_t>(row) * nchunks + lane + 32 * i, o);
-        }
+        if (drop.thresh != 0) DropState::apply8(drop, kb[i], o);
         stg128(yr + i * 256, f32_to_bf16x8(o));
       }
     }
@@ -200,7 +200,10 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     }
     cp_async_wait<2>();  // everything but the two youngest groups has landed: this row is in its slot
     const long long off = static_cast<long long>(row) * cols + lane * 8;
-    const uint64_t grp0 = static_cast<uint64_t>(row) * nchunks + lane;  // dropout group of chunk i: grp0 + 32 i
+    const uint64_t word0 = static_cast<uint64_t>(row) * (nchunks >> 2);  // dropout stream word of the row's first element
+    uint32_t kin[NCH], kout[NCH];  // keep bits of this lane's chunks under the two dropouts
+    if (HAS_DIN) st_in.keep_bytes_row<NCH>(din, word0, nchunks, lane, kin);
+    if (dx_drop != nullptr && dout.thresh != 0) st_out.keep_bytes_row<NCH>(dout, word0, nchunks, lane, kout);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
@@ -208,7 +211,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         float d[8], xv[8];
         bf16x8_to_f32(lds128(slot(stage, 0, i)), d);
         bf16x8_to_f32(lds128(slot(stage, 1, i)), xv);
-        if (HAS_DIN) st_in.apply8(din, grp0 + 32 * i, d);
+        if (HAS_DIN) DropState::apply8(din, kin[i], d);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -234,7 +237,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         float d[8], xv[8], o[8];
         bf16x8_to_f32(lds128(slot(stage, 0, i)), d);
         bf16x8_to_f32(lds128(slot(stage, 1, i)), xv);
-        if (HAS_DIN) st_in.apply8(din, grp0 + 32 * i, d);  // (regenerated: one LN instance per step)
+        if (HAS_DIN) DropState::apply8(din, kin[i], d);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -242,9 +245,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         for (int j = 0; j < 8; ++j) o[j] = fmaf(d[j], rstd * g[j], fmaf(xv[j], cb, cc));
         stg128(dx + off + i * 256, f32_to_bf16x8(o));
         if (dx_drop != nullptr) {
-          if (dout.thresh != 0) {
-            st_out.apply8(dout, grp0 + 32 * i, o);
-          }
+          if (dout.thresh != 0) DropState::apply8(dout, kout[i], o);
           stg128(dx_drop + off + i * 256, f32_to_bf16x8(o));
         }
       }
@@ -432,6 +433,7 @@ extern "C" int mh_layernorm_fwd(const void* x, const float* gamma, const float* 
                                 float* rstd, int rows, int cols, float eps, float p_drop, uint64_t seed,
                                 uint32_t site, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm: bad shape %d x %d", rows, cols);
+  MH_CHECK(!(p_drop > 0.f) || cols % 32 == 0, "layernorm: dropout needs cols %% 32 == 0 (one dropout stream word = 32 elements), got %d", cols);
   MH_CHECK(x != nullptr && y != nullptr && gamma != nullptr && beta != nullptr && mean != nullptr && rstd != nullptr,
            "layernorm: null pointer");
   MH_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
@@ -457,6 +459,7 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
                                 int cols, float p_in, uint64_t seed_in, uint32_t site_in, float p_out,
                                 uint64_t seed_out, uint32_t site_out, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm_bwd: bad shape %d x %d", rows, cols);
+  MH_CHECK(!(p_in > 0.f || p_out > 0.f) || cols % 32 == 0, "layernorm_bwd: dropout needs cols %% 32 == 0, got %d", cols);
   MH_CHECK(dy != nullptr && x != nullptr && gamma != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr &&
                dgamma != nullptr && dbeta != nullptr,
            "layernorm_bwd: null pointer");

@@ -190,16 +190,21 @@ __global__ void gather_labels_kernel(const long long* __restrict__ label, const 
   if (i < n_idx) dst[i] = idx[i] >= 0 ? label[idx[i]] : -100;
 }
 
-// y = x * keep(seed, site) / (1 - p), element index = row * cols + col (the GEMM-epilogue indexing)
-__global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long groups,
+// y = x * keep(seed, site) * scale, element index = row * cols + col (the GEMM-epilogue indexing): one dropout stream
+// word (32 consecutive elements) per thread
+__global__ void dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long words,
                                      const DropCfg drop) {
   const DropState dstate(drop);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < words;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float v[8];
-    bf16x8_to_f32(ldg128(x + i * 8), v);
-    dstate.apply8(drop, static_cast<uint64_t>(i), v);
-    stg128(y + i * 8, f32_to_bf16x8(v));
+    const uint32_t kw = drop.thresh != 0 ? dstate.keep32(drop, static_cast<uint64_t>(i)) : 0xffffffffu;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+      bf16x8_to_f32(ldg128(x + i * 32 + q * 8), v);
+      if (drop.thresh != 0) DropState::apply8(drop, kw >> (8 * q), v);
+      stg128(y + i * 32 + q * 8, f32_to_bf16x8(v));
+    }
   }
 }
 
@@ -306,9 +311,9 @@ extern "C" int mh_gather_labels(const long long* label, const int* idx, long lon
 
 extern "C" int mh_dropout_apply(const void* x, void* y, int rows, int cols, float p_drop, uint64_t seed, uint32_t site,
                                 void* stream) {
-  MH_CHECK(cols % 8 == 0 && p_drop > 0.f, "dropout_apply: cols %% 8 and p > 0 required");
-  const long long groups = static_cast<long long>(rows) * (cols / 8);
-  dropout_apply_kernel<<<ew_grid(groups, 256), 256, 0, ST>>>(CBF(x), BF(y), groups, make_drop(p_drop, seed, site));
+  MH_CHECK(cols % 32 == 0 && p_drop > 0.f, "dropout_apply: cols %% 32 (one dropout stream word = 32 elements) and p > 0 required");
+  const long long words = static_cast<long long>(rows) * (cols / 32);
+  dropout_apply_kernel<<<ew_grid(words, 256), 256, 0, ST>>>(CBF(x), BF(y), words, make_drop(p_drop, seed, site));
   MH_LAUNCH_CHECK();
   ++g_launches;
   return 0;

@@ -47,11 +47,6 @@ struct AttnParams {
 // byte offset of the 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] tile
 __device__ __forceinline__ uint32_t swz(int r, int ch) { return r * 128 + ((ch ^ (r & 7)) << 4); }
 
-// 16-byte store to a 32-bit shared-window address (no 64-bit generic pointer arithmetic in the hot loops)
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 // rare path of the forward softmax (lazy rescaling): kept out of line so the hot loop stays small
 __device__ __noinline__ void rescale_o_rows(uint32_t tmem_o_lane, float alpha) {
 #pragma unroll 1

@@ -173,6 +173,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   // dropout stream position of this thread's row (element (row, col) lives in word row * N/32 + col/32, bit col % 32)
   const uint64_t drop_base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N >> 5) + static_cast<uint64_t>(n0 >> 5);
   const DropState dstate(p.drop);  // (device step counter: one L1-resident load per tile)
+  const uint32_t stg_s = smem_u32(stg);
+  const float drop_s = (EPI == MH_EPI_GELU && p.drop.thresh != 0) ? p.drop.scale : 1.f;
+  const float drop_lg = (EPI == MH_EPI_GELU && p.drop.thresh != 0) ? log2f(p.drop.scale) : 0.f;
   if (active) {
     auto sub_chunk = [&](int s) {
       const int col_in_tile = e.grp * CG + s * 32;
@@ -193,38 +196,48 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
         const int ch = s * 4 + q;  // 16-byte chunk of the staging row
         uint8_t* slot = stg + stg_off<ROWB>(e.r_tile, ch);
+        const uint32_t slot_s = stg_s + stg_off<ROWB>(e.r_tile, ch);  // (shared-window address: STS / LDS, no generic ST.E)
         if (EPI == MH_EPI_BF16 || EPI == MH_EPI_GELU || EPI == MH_EPI_RES) {
           if (p.bias != nullptr && col_ok) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            unpack2f(fadd2(pack2f(v[0], v[1]), pack2f(b0.x, b0.y)), v[0], v[1]);
+            unpack2f(fadd2(pack2f(v[2], v[3]), pack2f(b0.z, b0.w)), v[2], v[3]);
+            unpack2f(fadd2(pack2f(v[4], v[5]), pack2f(b1.x, b1.y)), v[4], v[5]);
+            unpack2f(fadd2(pack2f(v[6], v[7]), pack2f(b1.z, b1.w)), v[6], v[7]);
           }
         }
         if (EPI == MH_EPI_GELU) {
           // the reference evaluates GELU in fp32 on the half-precision fc1 output
           // (fairseq_code/gelu.py:35 under autocast): round first, then activate.
           const uint4 pre = f32_to_bf16x8(v);
-          if (p.has_aux_out) *reinterpret_cast<uint4*>(slot) = pre;
+          if (p.has_aux_out) sts128(slot_s, pre);
           bf16x8_to_f32(pre, v);
-          gelu_erf8(v);
+          gelu_erf8(v, drop_s, drop_lg);  // (the dropout keep-scale rides along in the exponent: no multiply later)
         }
         if (EPI == MH_EPI_DGELU) {
           float pre[8];
-          bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), pre);
+          bf16x8_to_f32(lds128_plain(slot_s), pre);
           gelu_erf_grad_mul8(v, pre);
         }
         if (HAS_DROP) {
-          if (p.drop.thresh != 0) DropState::apply8(p.drop, kw >> (8 * q), v);
+          if (p.drop.thresh != 0) {
+            if (EPI == MH_EPI_GELU) {  // already scaled
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = ((kw >> (8 * q)) & (1u << j)) ? v[j] : 0.f;
+            } else {
+              DropState::apply8(p.drop, kw >> (8 * q), v);
+            }
+          }
         }
         if (EPI == MH_EPI_RES || EPI == MH_EPI_ADD) {
           float a[8];
-          bf16x8_to_f32(*reinterpret_cast<const uint4*>(slot), a);
+          bf16x8_to_f32(lds128_plain(slot_s), a);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += a[j];
+          for (int j = 0; j < 4; ++j) unpack2f(fadd2(pack2f(v[2 * j], v[2 * j + 1]), pack2f(a[2 * j], a[2 * j + 1])), v[2 * j], v[2 * j + 1]);
         }
         o4[q] = f32_to_bf16x8(v);
-        if (!(EPI == MH_EPI_GELU && p.has_aux_out)) *reinterpret_cast<uint4*>(slot) = o4[q];
+        if (!(EPI == MH_EPI_GELU && p.has_aux_out)) sts128(slot_s, o4[q]);
       }
       if (EPI == MH_EPI_GELU && p.has_aux_out) {
         if (s == 0) {

@@ -256,6 +256,17 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// 16-byte store to a 32-bit shared-window address (no 64-bit generic pointer arithmetic in the hot loops)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// (the TMA writes of an aux-in tile are ordered by its mbarrier wait, which carries a memory clobber)
+__device__ __forceinline__ uint4 lds128_plain(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 // ------------------------------------------------------------------ packed fp32 (two lanes per instruction: FFMA2 / FADD2 / FMUL2)
 __device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
   uint64_t r;
@@ -299,22 +310,27 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 // on two values per FFMA2.  Written in na = -|x| (one OR with the sign bit per value), so neither fabs nor negations
 // are needed: p(a) = c0 - c1 na + c2 na^2 - c3 na^3 + c4 na^4, exponent = P na - 1, gelu = max(x, 0) + na e.
 // 6 instructions per value (scalar: 9); the GELU / dGELU GEMM epilogues are issue-bound, see gemm_sm100.cu.
-__device__ __forceinline__ uint64_t erfc_half_scaled2(uint64_t na2) {  // (0.5 erfc(|x| / sqrt 2)) x 2, argument -|x|
+// lg = log2 of an optional output scale s (dropout keep-scale): 2^(... - 1 + lg) = s * 0.5 erfc(...), free of charge
+__device__ __forceinline__ uint64_t erfc_half_scaled2(uint64_t na2, float lg = 0.f) {  // s * (0.5 erfc(|x| / sqrt 2)) x 2, argument -|x|
   uint64_t p = pack2f(4.88221852e-04f, 4.88221852e-04f);
   p = ffma2(p, na2, pack2f(7.19561887e-03f, 7.19561887e-03f));
   p = ffma2(p, na2, pack2f(5.21302448e-02f, 5.21302448e-02f));
   p = ffma2(p, na2, pack2f(-4.59620056e-01f, -4.59620056e-01f));
   p = ffma2(p, na2, pack2f(1.15099005e+00f, 1.15099005e+00f));
   float t0, t1;
-  unpack2f(ffma2(p, na2, pack2f(-1.0f, -1.0f)), t0, t1);
+  unpack2f(ffma2(p, na2, pack2f(lg - 1.0f, lg - 1.0f)), t0, t1);
   return pack2f(ex2_approx(t0), ex2_approx(t1));
 }
-__device__ __forceinline__ void gelu_erf8(float (&v)[8]) {
+// v[j] = s * gelu(v[j]), s = 2^lg > 0 (s = 1: lg = 0):  s gelu(x) = max(s x, 0) + na (s e)
+__device__ __forceinline__ void gelu_erf8(float (&v)[8], float s = 1.f, float lg = 0.f) {
+  const uint64_t s2 = pack2f(s, s);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float x0 = v[2 * k], x1 = v[2 * k + 1];
     const uint64_t na2 = pack2f(__uint_as_float(__float_as_uint(x0) | 0x80000000u), __uint_as_float(__float_as_uint(x1) | 0x80000000u));
-    unpack2f(ffma2(na2, erfc_half_scaled2(na2), pack2f(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), v[2 * k], v[2 * k + 1]);
+    float y0, y1;
+    unpack2f(fmul2(pack2f(x0, x1), s2), y0, y1);
+    unpack2f(ffma2(na2, erfc_half_scaled2(na2, lg), pack2f(fmaxf(y0, 0.f), fmaxf(y1, 0.f))), v[2 * k], v[2 * k + 1]);
   }
 }
 // v[j] *= d gelu / dx at pre[j]:  Phi(x) + x phi(x),  Phi = 0.5 + copysign(0.5 - e, x),  phi = 0.39894228 2^(-0.72134752 x^2)

@@ -64,6 +64,10 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   int stage = 0;
   for (int row = warp_global; row < rows; row += nwarps) {
     issue(row + 2 * nwarps, stage + 2 >= LNB_STAGES ? stage + 2 - LNB_STAGES : stage + 2);
+    // keep bits of this lane's chunks (bit-sliced dropout: 32 decisions per generated word), produced while the row is
+    // still in flight -- the kernel is latency-bound, the Philox rounds are free here
+    uint32_t kb[NCH];
+    if (drop.thresh != 0) dstate.keep_bytes_row<NCH>(drop, static_cast<uint64_t>(row) * (nchunks >> 2), nchunks, lane, kb);
     cp_async_wait<2>();
     float v[NCH][8];
     float s = 0.f;
@@ -94,8 +98,6 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
     }
     __nv_bfloat16* yr = y + static_cast<long long>(row) * cols + lane * 8;
     const float nmr = -mean * rstd;
-    uint32_t kb[NCH];  // keep bits of this lane's chunks (bit-sliced dropout: 32 decisions per generated word)
-    if (drop.thresh != 0) dstate.keep_bytes_row<NCH>(drop, static_cast<uint64_t>(row) * (nchunks >> 2), nchunks, lane, kb);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       if (EXACT || lane + 32 * i < nchunks) {
@@ -198,12 +200,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       nmean = __ldg(mean_in + row + nwarps);
       nrstd = __ldg(rstd_in + row + nwarps);
     }
-    cp_async_wait<2>();  // everything but the two youngest groups has landed: this row is in its slot
-    const long long off = static_cast<long long>(row) * cols + lane * 8;
     const uint64_t word0 = static_cast<uint64_t>(row) * (nchunks >> 2);  // dropout stream word of the row's first element
-    uint32_t kin[NCH], kout[NCH];  // keep bits of this lane's chunks under the two dropouts
+    uint32_t kin[NCH], kout[NCH];  // keep bits of this lane's chunks under the two dropouts (generated under the loads)
     if (HAS_DIN) st_in.keep_bytes_row<NCH>(din, word0, nchunks, lane, kin);
     if (dx_drop != nullptr && dout.thresh != 0) st_out.keep_bytes_row<NCH>(dout, word0, nchunks, lane, kout);
+    cp_async_wait<2>();  // everything but the two youngest groups has landed: this row is in its slot
+    const long long off = static_cast<long long>(row) * cols + lane * 8;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {

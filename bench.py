@@ -213,6 +213,7 @@ def workload_config(args, per_gpu_batch=None):
             "mode": args.mode, "frame_ms": args.frame, "feat_dim": 80 if args.frame == 20 else 40,
             "per_gpu_batch": B, "frames": args.frames, "accum": args.accum, "global_batch": B * args.accum * args.gpus,
             "parallelism": f"dp{args.gpus}",
+            "dp_transport": (os.environ.get("MH_DP_TRANSPORT", "peer") if args.gpus > 1 else None),
             "l2": ("bf16 weights (180 MB) + per-layer activations stream through HBM every forward: > 126 MB L2, no flush needed"
                    if args.mode == "extract" else
                    "every step streams ~1.6 GB of fp32 master / gradient / moment state (fused Adam) plus the activations "

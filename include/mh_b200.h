@@ -22,12 +22,14 @@ int mh_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long mh_launch_count(void);
 
-/* Dropout streams: every dropout decision is a 16-bit lane of
- *   Philox4x32-7(key = seed, counter = (element/8, *offset, site)),
- * kept iff lane >= round(p * 65536).  `offset` is an optional device-resident step counter (NULL
- * disables it) so that CUDA-graph replays draw fresh masks: bump it once per step with
- * mh_counter_add.  Forward and backward of one step must see the same counter value.  (The seed
- * is the Philox key: its round keys are derived on the host and travel as kernel parameters.) */
+/* Dropout streams (reference: nn.Dropout / FairseqDropout at module.py:121-131, forward_multihead_attention.py:64-66).
+ * A stream is cut into words of 32 consecutive elements; element i of word w is kept iff its 12-bit number
+ *   R = bit-sliced Philox4x32-7(key = seed, counter = (2 w + call, *offset, site))
+ * is >= round(p * 4096); survivors are scaled by 4096 / (4096 - thr) (p is quantised to 1/4096).  `offset` is an
+ * optional device-resident step counter (NULL disables it) so that CUDA-graph replays draw fresh masks: bump it once
+ * per step with mh_counter_add.  Forward and backward of one step must see the same counter value.  (The seed is the
+ * Philox key: its round keys are derived on the host and travel as kernel parameters.)  Kernels with a dropout
+ * argument need their column count to be a multiple of 32. */
 int mh_set_dropout_offset_ptr(const unsigned long long* device_counter);
 int mh_counter_add(unsigned long long* device_counter, unsigned long long v, void* stream);
 
@@ -237,6 +239,33 @@ int mh_sumsq(const float* x, long long n, float* out, void* stream);
 int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, const unsigned long long* step /* device, 1-based */, float grad_scale,
                  float max_norm, const float* sumsq, int zero_grad, void* bf16_shadow, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory -- replaces the reduce_add_coalesced / broadcast_coalesced
+ * that nn.DataParallel runs per step (upstream/melhubert/pretrain_expert.py:28-30, runner.py:372-373).
+ *   grads[p], flags[p] (p < world): device pointers, valid on THIS device, to rank p's flat fp32 gradient buffer and to
+ *   its flag array (8 x u64, zero-initialised); entry `rank` is the local one.  state: local 2 x u64, zero-initialised.
+ *   A bucket [start, start + count) (multiples of 4 elements) is cut into `world` shards:
+ *     mh_peer_reduce_scatter : this rank's shard <- sum over ranks 0..world-1 (fixed order), pulled over NVLink
+ *     mh_peer_all_gather     : every other shard <- the owner's reduced copy
+ *     mh_peer_barrier_sum    : barrier across ranks (call before the optimizer reuses the buffer); with n > 0 also
+ *                              vals[0..n) <- sum over ranks (n <= 16; mailboxes[p]: rank p's 2 x 8 x 16 float mailbox)
+ *   All ranks must issue the same sequence of these three calls.  ctas <= 0 picks a default; the kernels are sized to
+ *   co-reside with the persistent GEMM / attention CTAs (128 threads, <= 56 registers, no shared memory).
+ * ------------------------------------------------------------------------------------- */
+int mh_peer_reduce_scatter(void* const* grads, void* const* flags, void* state, long long start, long long count,
+                           int rank, int world, int ctas, void* stream);
+int mh_peer_all_gather(void* const* grads, void* const* flags, void* state, long long start, long long count,
+                       int rank, int world, int ctas, void* stream);
+/* Copy-engine variants (default transport): the same exchange with the NVLink pulls issued as cudaMemcpyAsync on the
+ * peer-mapped pointers (DMA, no SMs) and one light local kernel that adds the staged shards in rank order.
+ * staging: local scratch of >= (world - 1) * (shard length rounded up to 32) floats. */
+int mh_peer_reduce_scatter_ce(void* const* grads, void* const* flags, void* state, float* staging, long long staging_elems,
+                              long long start, long long count, int rank, int world, void* stream);
+int mh_peer_all_gather_ce(void* const* grads, void* const* flags, void* state, long long start, long long count, int rank,
+                          int world, void* stream);
+int mh_peer_barrier_sum(void* const* grads, void* const* flags, void* const* mailboxes, void* state, float* vals, int n,
+                        int rank, int world, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Front-end: batched Kaldi-compatible log-mel filterbank, replacing the host-side

@@ -488,7 +488,7 @@ struct AttnBwdParams {
 // (dS may be overwritten): no further barriers are needed for the single P / dS tiles.
 constexpr int BWD_DQ_STAGE = 128 * 64 * 4;
 constexpr int BWD_QST = 3;  // Q / dO ring depth: S(n+2) is issued in the middle of iteration n+1
-constexpr int BWD_KVLEN_CACHE = 256;
+constexpr int BWD_KVLEN_CACHE = 128;  // (512 B: keeps 1 KB of the SM's shared memory free, enough for a co-resident peer-exchange CTA, peer.cu)
 constexpr int BWD_SMEM = TILE_BYTES * (2 + 2 * BWD_QST + 2 + 2) + BWD_DQ_STAGE + 1024 + 256 + BWD_KVLEN_CACHE * 4;
 constexpr int BWD_THREADS = 608;  // warps 0-15 compute, 16 = TMA loads, 17 = MMA, 18 = dQ reduce-add
 

@@ -357,6 +357,39 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, 
           _p(shadow), _s())
 
 
+# ------------------------------------------------------------------------------ peer-memory gradient exchange
+def _ptr_array(ptrs):
+    import ctypes
+
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(x)) for x in ptrs])
+
+
+def peer_reduce_scatter(grad_ptrs, flag_ptrs, state, start, count, rank, world, ctas=0):
+    _call("mh_peer_reduce_scatter", _ptr_array(grad_ptrs), _ptr_array(flag_ptrs), _p(state), c_longlong(start),
+          c_longlong(count), c_int(rank), c_int(world), c_int(ctas), _s())
+
+
+def peer_all_gather(grad_ptrs, flag_ptrs, state, start, count, rank, world, ctas=0):
+    _call("mh_peer_all_gather", _ptr_array(grad_ptrs), _ptr_array(flag_ptrs), _p(state), c_longlong(start),
+          c_longlong(count), c_int(rank), c_int(world), c_int(ctas), _s())
+
+
+def peer_reduce_scatter_ce(grad_ptrs, flag_ptrs, state, staging, start, count, rank, world):
+    _call("mh_peer_reduce_scatter_ce", _ptr_array(grad_ptrs), _ptr_array(flag_ptrs), _p(state), _p(staging),
+          c_longlong(staging.numel()), c_longlong(start), c_longlong(count), c_int(rank), c_int(world), _s())
+
+
+def peer_all_gather_ce(grad_ptrs, flag_ptrs, state, start, count, rank, world):
+    _call("mh_peer_all_gather_ce", _ptr_array(grad_ptrs), _ptr_array(flag_ptrs), _p(state), c_longlong(start),
+          c_longlong(count), c_int(rank), c_int(world), _s())
+
+
+def peer_barrier_sum(grad_ptrs, flag_ptrs, mail_ptrs, state, vals, rank, world):
+    n = 0 if vals is None else vals.numel()
+    _call("mh_peer_barrier_sum", _ptr_array(grad_ptrs), _ptr_array(flag_ptrs), _ptr_array(mail_ptrs), _p(state), _p(vals),
+          c_int(n), c_int(rank), c_int(world), _s())
+
+
 def set_dropout_offset(counter):
     """Register a device uint64 counter that is mixed into every dropout seed (None disables)."""
     _call("mh_set_dropout_offset_ptr", _p(counter))

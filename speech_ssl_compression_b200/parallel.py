@@ -1,12 +1,20 @@
-"""Data parallelism: one process per GPU, NCCL over NVLink (replaces the reference's
+"""Data parallelism: one process per GPU over NVLink / NVSwitch (replaces the reference's
 single-process ``nn.DataParallel``, ``upstream/melhubert/pretrain_expert.py:28-30``).
 
 Gradients live in ONE flat fp32 buffer (``param.grad`` are views into it, so the wgrad GEMMs
 accumulate straight into it).  Each encoder layer owns a contiguous slice; when a layer's
-backward returns, its slice is all-reduced on a side stream while the remaining layers keep
+backward returns, its slice is summed over the ranks on a side stream while the remaining layers keep
 computing -- the last bucket (everything outside the layers) is reduced in ``finish()``.
 The cross-entropy normaliser is made global with a 2-float all-reduce (``all_reduce_sum``),
 which reproduces DataParallel's gather-then-mean loss semantics.
+
+Two transports for the buckets (``MH_DP_TRANSPORT``):
+  * ``peer`` (default on CUDA): own reduce-scatter / all-gather kernels that pull over peer-mapped gradient buffers
+    (``csrc/peer.cu``; CUDA IPC handles exchanged once through the process group).  Their CTAs are small enough to
+    share SMs with the persistent GEMM / attention kernels, which ``ncclAllReduce`` CTAs cannot -- NCCL on the side
+    stream cost 1.4-1.7 ms per step (SCALE_r01) by knocking persistent GEMM clusters into a second wave.
+  * ``nccl``: ``torch.distributed.all_reduce`` per bucket (also what the CPU / gloo tests exercise).
+torch.distributed (NCCL / gloo) stays the control plane: rendezvous, the initial parameter broadcast, handle exchange.
 """
 import os
 
@@ -81,22 +89,96 @@ class FlatBuffers:
         return self.offsets[lo], end
 
 
+class PeerGradExchange:
+    """Peer-memory transport: every rank maps every other rank's flat gradient buffer, flag array and mailbox
+    (CUDA IPC), then sums buckets with ``mh_peer_reduce_scatter`` / ``mh_peer_all_gather`` (csrc/peer.cu)."""
+
+    def __init__(self, flat_grad, rank, world):
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self.rank, self.world = rank, world
+        self.use_sm = os.environ.get("MH_DP_TRANSPORT") == "peer-sm"
+        self.staging = None  # copy-engine transport: (world - 1) staged peer shards of the largest bucket
+        dev = flat_grad.device
+        # own allocations (cudaMalloc blocks of their own: an IPC handle exports the whole block)
+        self.flags = torch.zeros(8, device=dev, dtype=torch.int64)
+        self.mail = torch.zeros(2 * 8 * 16, device=dev, dtype=torch.float32)
+        self.state = torch.zeros(2, device=dev, dtype=torch.int64)
+        torch.cuda.synchronize()
+        mine = []
+        for t in (flat_grad, self.flags, self.mail):
+            fn, args = reduce_tensor(t)
+            mine.append((fn, list(args)))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        self._keep = []  # peer-mapped tensors must stay alive as long as their pointers are used
+        self.grad_ptrs, self.flag_ptrs, self.mail_ptrs = [], [], []
+        for p in range(world):
+            if p == rank:
+                ts = (flat_grad, self.flags, self.mail)
+            else:
+                ts = []
+                for fn, args in everyone[p]:
+                    # rebuild_cuda_tensor(cls, size, stride, offset, storage_cls, dtype, storage_device, handle, ...):
+                    # open the handle on THIS device -- the mapping is then reachable from our kernels through peer
+                    # access (cudaIpcMemLazyEnablePeerAccess) without creating a context on the peer device
+                    args = list(args)
+                    args[6] = dev.index
+                    ts.append(fn(*args))
+                self._keep.append(ts)
+            self.grad_ptrs.append(ts[0].data_ptr())
+            self.flag_ptrs.append(ts[1].data_ptr())
+            self.mail_ptrs.append(ts[2].data_ptr())
+        dist.barrier()
+
+    def reduce_span(self, start, end):
+        from . import kernels as K
+
+        n = end - start
+        if self.use_sm:  # SM-driven pulls (A/B only)
+            K.peer_reduce_scatter(self.grad_ptrs, self.flag_ptrs, self.state, start, n, self.rank, self.world)
+            K.peer_all_gather(self.grad_ptrs, self.flag_ptrs, self.state, start, n, self.rank, self.world)
+            return
+        shard = ((n + self.world - 1) // self.world + 3) // 4 * 4
+        need = (self.world - 1) * ((shard + 31) // 32 * 32)
+        if self.staging is None or self.staging.numel() < need:
+            self.staging = torch.empty(need, device=self.flags.device, dtype=torch.float32)
+        K.peer_reduce_scatter_ce(self.grad_ptrs, self.flag_ptrs, self.state, self.staging, start, n, self.rank, self.world)
+        K.peer_all_gather_ce(self.grad_ptrs, self.flag_ptrs, self.state, start, n, self.rank, self.world)
+
+    def barrier(self, vals=None):
+        """Cross-rank barrier on the current stream; ``vals`` (<= 16 fp32, optional) is summed over the ranks in place."""
+        from . import kernels as K
+
+        K.peer_barrier_sum(self.grad_ptrs, self.flag_ptrs, self.mail_ptrs, self.state, vals, self.rank, self.world)
+
+
 class DataParallelB200:
     def __init__(self, model, overlap=True):
         self.model = model
         self.rank, self.world_size = init_distributed()
-        self.overlap = overlap
+        self.overlap = overlap and os.environ.get("MH_DP_OVERLAP", "1") != "0"
         self.enabled = self.world_size > 1
         self.flat = None
         self._pending = []
         self._comm_stream = None
         self.sync = True  # False while a non-final micro-batch of a gradient-accumulation step runs (no all-reduce)
+        self.peer = None  # PeerGradExchange once attached (CUDA, MH_DP_TRANSPORT != nccl)
 
     # -- loss normaliser ---------------------------------------------------------------------
     def all_reduce_sum(self, t):
         if self.enabled:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            if self.peer is not None and t.dtype == torch.float32 and t.numel() <= 16 and t.is_contiguous():
+                self._peer_on_main(lambda: self.peer.barrier(t))  # (no NCCL kernel in the step at all)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
+
+    def _peer_on_main(self, fn):
+        """Peer kernels share ONE epoch counter per rank, so they must execute in issue order.  Calls from the main
+        stream need no explicit edge: ``finish()`` joined the communication stream at the end of the previous step
+        (and a bucket reduction makes the communication stream wait for the main stream first, ``_reduce_span``)."""
+        fn()
 
     # -- gradient buckets --------------------------------------------------------------------
     def attach(self, flat: FlatBuffers):
@@ -125,18 +207,25 @@ class DataParallelB200:
             rest.append((cur, flat.total))
         self._rest_spans = rest
         if self.enabled and torch.cuda.is_available():
-            self._comm_stream = torch.cuda.Stream()
+            self._comm_stream = torch.cuda.Stream(priority=-1)
+            if os.environ.get("MH_DP_TRANSPORT", "peer") not in ("nccl", "none") and flat.flat_grad.is_cuda:
+                self.peer = PeerGradExchange(flat.flat_grad, self.rank, self.world_size)
 
     def _reduce_span(self, span):
         if not self.enabled or span is None or not self.sync:
             return
+        if os.environ.get("MH_DP_TRANSPORT") == "none":  # timing experiments only: no gradient exchange at all
+            return
         buf = self.flat.flat_grad[span[0]:span[1]]
+        reduce = (lambda: self.peer.reduce_span(span[0], span[1])) if self.peer is not None else \
+            (lambda: dist.all_reduce(buf, op=dist.ReduceOp.SUM))
         if self._comm_stream is not None and self.overlap:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                reduce()
+            self._comm_used = True
         else:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            reduce()
 
     def _make_hook(self, span):
         def hook(layer):
@@ -149,5 +238,8 @@ class DataParallelB200:
             return
         for span in self._rest_spans:
             self._reduce_span(span)
-        if self._comm_stream is not None:
+        if self._comm_stream is not None and getattr(self, "_comm_used", False):
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._comm_used = False
+        if self.peer is not None:
+            self.peer.barrier()  # every peer has pulled what it needs: the optimizer may zero the buffer

@@ -82,6 +82,8 @@ def main():
     single = TrainStep(expert(False), Bg, T, D, use_graph=False)
     multi = TrainStep(expert(True), Bl, T, D, use_graph=False)
     assert multi.dp.enabled and multi.dp.world_size == world
+    assert (multi.dp.peer is not None) == (os.environ.get("MH_DP_TRANSPORT", "peer") != "nccl")
+    assert multi.dp.peer is None or multi.dp.peer.use_sm == (os.environ.get("MH_DP_TRANSPORT") == "peer-sm")
     # (1) one micro-batch, then two accumulated ones
     for n_micro in (1, 2):
         single.flat.flat_grad.zero_()

@@ -209,7 +209,19 @@ class DataParallelB200:
         if self.enabled and torch.cuda.is_available():
             self._comm_stream = torch.cuda.Stream(priority=-1)
             if os.environ.get("MH_DP_TRANSPORT", "peer") not in ("nccl", "none") and flat.flat_grad.is_cuda:
-                self.peer = PeerGradExchange(flat.flat_grad, self.rank, self.world_size)
+                # the mapping can fail for reasons outside this code (no peer access between the devices, IPC disabled
+                # in the container): all ranks then agree to fall back to NCCL for the buckets -- loudly
+                try:
+                    peer, err = PeerGradExchange(flat.flat_grad, self.rank, self.world_size), None
+                except Exception as e:  # noqa: BLE001
+                    peer, err = None, e
+                ok = torch.tensor([1.0 if peer is not None else 0.0], device=flat.flat_grad.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok) == 1.0:
+                    self.peer = peer
+                else:
+                    print(f"[DataParallelB200] rank {self.rank}: peer-memory gradient exchange unavailable "
+                          f"({err if err is not None else 'another rank failed'}); using NCCL all-reduce for the buckets", flush=True)
 
     def _reduce_span(self, span):
         if not self.enabled or span is None or not self.sync:

@@ -274,8 +274,15 @@ def live_rooflines(run_once, peaks, B, T):
 
     K.gemm, K.attn_fwd, K.attn_bwd = timed, timed_af, timed_ab
     try:
+        # how long the HOST needs to enqueue one bracketed pass (untimed rehearsal), then hold the stream for longer
+        # than that while the measured pass is queued (see docstring)
         torch.cuda.synchronize()
-        torch.cuda._sleep(int(0.06 * 1.9e9))  # hold the stream while the host enqueues the pass (see docstring)
+        t0 = time.perf_counter()
+        run_once()
+        host_s = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        rec.clear(); arec.clear()
+        torch.cuda._sleep(int(max(0.06, 1.5 * host_s) * 1.9e9))
         run_once()
         torch.cuda.synchronize()
     finally:
@@ -343,7 +350,7 @@ def live_rooflines(run_once, peaks, B, T):
     attn = {"bound": "tensor", "kernel": "mh::attn_fwd2_kernel / mh::attn_bwd_kernel (+ attn_delta, dq_finish, dQ workspace memset: "
                                          "everything one mh_attn_fwd / mh_attn_bwd call launches)",
             "achieved": aach, "peak": peak, "unit": "TFLOP/s", "frac": aach / peak, "traffic": None, "peak_source": peak_src,
-            "calls": len(arec), "timing": "CUDA-event pair per C-ABI call on the launching stream",
+            "calls": len(arec), "timing": "CUDA-event pair per C-ABI call on the launching stream, pass pre-queued behind a spin kernel",
             "attention_ms_per_step": ams, "attention_tflop_per_step": aflops / 1e12,
             "by_pass": {k: {"calls": v[0], "tflops": v[1] / v[2] / 1e9, "us_per_call": v[2] / v[0] * 1e3} for k, v in aby.items()},
             "frac_of_burst_peak": aach / burst,

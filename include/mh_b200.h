@@ -236,6 +236,17 @@ int mh_col_abs_sums(const float* w, long long ld, double* out, int rows, int col
  * pass -- the next step's GEMM operands, replacing the per-step casts of runner.py:363's autocast.
  * ------------------------------------------------------------------------------------- */
 int mh_sumsq(const float* x, long long n, float* out, void* stream);
+/* Weight-pruning mode (pytorch_code/prune.py:24-38: weight = weight_orig.masked_fill(~mask, 0) before every forward,
+ * gradients of pruned elements zeroed by its backward): `mask` is one byte per element of the flat buffer (0 = pruned,
+ * 4-byte aligned).  The masked variants ignore pruned gradients (norm and update) and write the EFFECTIVE parameters
+ * param * mask as the bf16 operand shadow and, optionally, as an fp32 copy (bias operands) -- replacing the 144
+ * per-forward mask applications.  mh_flat_effective builds the same two copies outside the optimizer. */
+int mh_sumsq_masked(const float* x, const uint8_t* mask, long long n, float* out, void* stream);
+int mh_adam_step_masked(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, const unsigned long long* step, float grad_scale,
+                        float max_norm, const float* sumsq, int zero_grad, void* bf16_shadow, const uint8_t* mask,
+                        float* effective, void* stream);
+int mh_flat_effective(const float* param, const uint8_t* mask, void* bf16_shadow, float* effective, long long n, void* stream);
 int mh_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, const unsigned long long* step /* device, 1-based */, float grad_scale,
                  float max_norm, const float* sumsq, int zero_grad, void* bf16_shadow, void* stream);

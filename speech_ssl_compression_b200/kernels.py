@@ -346,15 +346,28 @@ def col_abs_sums(w):
 
 
 # ------------------------------------------------------------------------------ optimizer
-def sumsq_add(x, out):
-    _call("mh_sumsq", _p(x), c_longlong(x.numel()), _p(out), _s())
+def sumsq_add(x, out, mask=None):
+    if mask is None:
+        _call("mh_sumsq", _p(x), c_longlong(x.numel()), _p(out), _s())
+    else:
+        _call("mh_sumsq_masked", _p(x), _p(mask), c_longlong(x.numel()), _p(out), _s())
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, weight_decay=0.0, grad_scale=1.0,
-              max_norm=0.0, sumsq=None, zero_grad=True, shadow=None):
-    _call("mh_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), c_longlong(param.numel()), _f(lr), _f(beta1),
-          _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq), c_int(int(zero_grad)),
-          _p(shadow), _s())
+              max_norm=0.0, sumsq=None, zero_grad=True, shadow=None, mask=None, effective=None):
+    if mask is None:
+        _call("mh_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), c_longlong(param.numel()), _f(lr), _f(beta1),
+              _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq), c_int(int(zero_grad)),
+              _p(shadow), _s())
+    else:
+        _call("mh_adam_step_masked", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), c_longlong(param.numel()), _f(lr),
+              _f(beta1), _f(beta2), _f(eps), _f(weight_decay), _p(step), _f(grad_scale), _f(max_norm), _p(sumsq),
+              c_int(int(zero_grad)), _p(shadow), _p(mask), _p(effective), _s())
+
+
+def flat_effective(param, mask, shadow, effective):
+    """shadow (bf16) / effective (fp32) <- param * mask over a whole flat buffer (mask None: plain copies)."""
+    _call("mh_flat_effective", _p(param), _p(mask), _p(shadow), _p(effective), c_longlong(param.numel()), _s())
 
 
 # ------------------------------------------------------------------------------ peer-memory gradient exchange

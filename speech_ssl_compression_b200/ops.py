@@ -103,10 +103,20 @@ def _shadow_operands(parts):
         fb._shadow_epoch = _EPOCH[0]
     kdim = parts[0][0].shape[1]
     w_off, b_off = off, None
+    masked = False
     for w, wm, b, bm in parts:
         fw, fbias = getattr(w, "_mh_flat", None), getattr(b, "_mh_flat", None) if b is not None else None
-        if wm is not None or bm is not None or b is None or fw is None or fbias is None or fw[0] is not fb or fbias[0] is not fb:
+        if b is None or fw is None or fbias is None or fw[0] is not fb or fbias[0] is not fb:
             return None
+        if wm is not None or bm is not None:
+            # prune masks: the shadow holds param * mask as long as the flat mask buffer mirrors these very mask tensors
+            if not fb.owners:
+                return None
+            if (wm is not None and not fb.masks_current(w, wm)) or (bm is not None and not fb.masks_current(b, bm)):
+                fb.sync_shadow()  # masks were replaced / edited since the last sync (prune event)
+                if (wm is not None and not fb.masks_current(w, wm)) or (bm is not None and not fb.masks_current(b, bm)):
+                    return None
+            masked = True
         if fw[1] != w_off or w.shape[1] != kdim or w.data_ptr() != fb.flat_param.data_ptr() + 4 * fw[1]:
             return None  # not adjacent, or the Parameter was re-pointed (surgery) since the buffers were built
         if b_off is None:
@@ -117,7 +127,8 @@ def _shadow_operands(parts):
         b_off += b.numel()
     n_total = sum(p[0].shape[0] for p in parts)
     wv = torch.as_strided(fb.flat_bf16, (n_total, kdim), (kdim, 1), off)
-    bv = torch.as_strided(fb.flat_param, (n_total,), (1,), parts[0][2]._mh_flat[1])
+    bv = torch.as_strided(fb.flat_eff if (masked or fb.flat_eff is not None) else fb.flat_param, (n_total,), (1,),
+                          parts[0][2]._mh_flat[1])
     return wv, bv
 
 
@@ -127,12 +138,20 @@ def _grad_of(p):
     return p.grad
 
 
+def _flat_masked(p):
+    """True when ``p`` lives in a FlatBuffers whose optimizer applies the prune masks (flat_mask built)."""
+    f = getattr(p, "_mh_flat", None)
+    return f is not None and f[0].flat_mask is not None
+
+
 def _wgrad(dy, x, lin, col0=0, ncols=None):
     """lin.weight.grad += dy[:, col0:col0+n]^T @ x  (masked);  lin.bias.grad += column sums."""
     w, wm = param_and_mask(lin, "weight")
     b, bm = param_and_mask(lin, "bias")
     n = w.shape[0] if ncols is None else ncols
     dyv = dy[:, col0:col0 + n] if (col0 or n != dy.shape[1]) else dy
+    if _flat_masked(w):
+        wm = bm = None  # the masked optimizer kernels drop the gradients of pruned elements (mh_adam_step_masked)
     if w.requires_grad:
         K.gemm(dyv, x, _grad_of(w), a_mn=True, b_mn=True, epilogue=K.EPI_F32, mask=wm)
     if b is not None and b.requires_grad:
@@ -151,6 +170,9 @@ def _wgrad_qkv(dqkv, x, mha, E):
     lins = (mha.q_proj, mha.k_proj, mha.v_proj)
     pw = [param_and_mask(l, "weight") for l in lins]
     pb = [param_and_mask(l, "bias") for l in lins]
+    if all(_flat_masked(w) for w, _ in pw):
+        pw = [(w, None) for w, _ in pw]
+        pb = [(b, None) for b, _ in pb]
     fused = all(w.requires_grad and m is None and w.grad is not None for w, m in pw)
     if fused:
         g = [w.grad for w, _ in pw]

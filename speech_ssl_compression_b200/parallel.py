@@ -55,6 +55,12 @@ class FlatBuffers:
         self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_bf16 = None  # bf16 shadow of flat_param (GEMM operands), kept current by the fused optimizer
+        # weight-pruning mode: one mask byte per element (0 = pruned) and the fp32 effective parameters param * mask
+        # (bias operands); built by refresh_masks() from the modules' <name>_mask buffers, consumed by the masked
+        # optimizer kernels -- replaces the reference's 144 per-forward masked_fill launches (prune.py:24-38)
+        self.flat_mask = self.flat_eff = None
+        self.owners = {}       # id(param) -> (module, parameter name), filled by bind_modules()
+        self._mask_sig = {}    # id(param) -> (mask data_ptr, mask version) of what flat_mask currently holds
         for p, o in zip(self.params, offs):
             view = self.flat_param[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
@@ -73,11 +79,48 @@ class FlatBuffers:
         self._shadow_epoch = ops._EPOCH[0]
         return self.flat_bf16
 
+    def bind_modules(self, root):
+        """Remember which module owns each flat parameter (needed to find its prune mask)."""
+        mine = {id(p) for p in self.params}
+        for mod in root.modules():
+            for name, p in mod._parameters.items():
+                if p is not None and id(p) in mine:
+                    self.owners[id(p)] = (mod, name)
+
+    def mask_of(self, p):
+        own = self.owners.get(id(p))
+        if own is None or not own[1].endswith("_orig"):
+            return None
+        return own[0]._buffers.get(own[1][:-5] + "_mask")
+
+    def refresh_masks(self):
+        """flat_mask <- the modules' current prune masks (all ones where a parameter has none)."""
+        masks = [(p, o, self.mask_of(p)) for p, o in zip(self.params, self.offsets)]
+        if not any(m is not None for _, _, m in masks):
+            self.flat_mask = self.flat_eff = None
+            self._mask_sig = {}
+            return
+        if self.flat_mask is None:
+            self.flat_mask = torch.ones(self.total, device=self.flat_param.device, dtype=torch.uint8)
+            self.flat_eff = torch.empty_like(self.flat_param)
+        self._mask_sig = {}
+        for p, o, m in masks:
+            if m is None:
+                self.flat_mask[o:o + p.numel()].fill_(1)
+            else:
+                self.flat_mask[o:o + p.numel()].copy_(m.reshape(-1))
+                self._mask_sig[id(p)] = (m.data_ptr(), m._version)
+
+    def masks_current(self, p, m):
+        return self._mask_sig.get(id(p)) == (m.data_ptr(), m._version)
+
     def sync_shadow(self):
         from . import kernels as K
 
         if self.flat_bf16 is not None:
-            K.to_bf16(self.flat_param, self.flat_bf16)
+            if self.owners:
+                self.refresh_masks()
+            K.flat_effective(self.flat_param, self.flat_mask, self.flat_bf16, self.flat_eff)
 
     def span(self, params):
         """(start, end) of the contiguous slice covering ``params`` (must be adjacent)."""

@@ -33,10 +33,12 @@ class FusedAdam:
     def step(self, grad_scale=1.0, max_norm=0.0):
         K.counter_add(self.step_count, 1)
         self.sumsq.zero_()
-        K.sumsq_add(self.flat.flat_grad, self.sumsq)
+        mask = self.flat.flat_mask  # weight-pruning mode: pruned elements get no gradient, operands are param * mask
+        K.sumsq_add(self.flat.flat_grad, self.sumsq, mask=mask)
         K.adam_step(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
                     lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
-                    grad_scale=grad_scale, max_norm=max_norm, sumsq=self.sumsq, zero_grad=True, shadow=self.shadow)
+                    grad_scale=grad_scale, max_norm=max_norm, sumsq=self.sumsq, zero_grad=True, shadow=self.shadow,
+                    mask=mask, effective=self.flat.flat_eff if mask is not None else None)
         ops.bump_weight_epoch()  # operands that are NOT views of the shadow (pruned / masked weights) are rebuilt
         self.flat._shadow_epoch = ops._EPOCH[0]  # ... the shadow itself is current
 
@@ -150,6 +152,7 @@ class TrainStep:
         if self.teacher is not None:
             self.teacher.static_rows = True
         self.flat = FlatBuffers(trainable_params(expert))
+        self.flat.bind_modules(expert)
         self.opt = FusedAdam(self.flat, lr, betas, eps, weight_decay)
         self.opt.param_order = list(expert.parameters())  # runner.py:314 Adam(expert.parameters())
         self.dp = getattr(expert, "dp", None)
@@ -304,6 +307,8 @@ class TrainStep:
              self.loss_acc]
         if f.flat_bf16 is not None:
             t.append(f.flat_bf16)
+        if f.flat_eff is not None:
+            t.append(f.flat_eff)
         return [(x, x.clone()) for x in t], np.random.get_state()
 
     @staticmethod
@@ -317,6 +322,11 @@ class TrainStep:
         accumulating, one for the final micro-batch + optimizer).  The warm-up runs real optimizer steps on whatever
         batch is loaded, so parameters, Adam state, step / dropout counters and the NumPy stream are put back afterwards:
         capturing changes nothing the training run can see."""
+        if getattr(self.flat, "_shadow_epoch", None) != ops._EPOCH[0]:
+            # parameters / prune masks changed outside the optimizer since the operand shadow was written: rebuild it
+            # NOW, so that the snapshot below holds (and later restores) a current shadow
+            self.flat.sync_shadow()
+            self.flat._shadow_epoch = ops._EPOCH[0]
         snap = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

@@ -89,6 +89,11 @@ int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, uint8
 int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                 const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
                 float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* mh_attn_bwd zeroes dq_acc itself; the _prezeroed variant expects the caller to have done so (e.g. on a side stream,
+ * overlapped with the GEMMs in front of it). */
+int mh_attn_bwd_prezeroed(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
+                float p_drop, uint64_t seed, uint32_t site, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNorm family (module.py:121-123,129-131,232-236: dropout -> +residual -> LayerNorm is

@@ -1012,9 +1012,28 @@ extern "C" int mh_attn_trace_read(long long* host_out) {  // debug builds only: 
 }
 #endif
 
+static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                         const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, void* stream);
+
 extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                            const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
                            int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site, true,
+                       stream);
+}
+
+// same, for a dq_acc workspace the caller has ALREADY zeroed (e.g. on a side stream under the preceding GEMMs)
+extern "C" int mh_attn_bwd_prezeroed(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                                     const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
+                                     int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site, false,
+                       stream);
+}
+
+static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                         const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, void* stream) {
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_bwd: bad shape B=%d T=%d heads=%d", B, T, heads);
   MH_CHECK(!(p_drop > 0.f) || keep_bits != nullptr, "attn_bwd: dropout needs the keep bits written by mh_attn_fwd");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1039,7 +1058,7 @@ extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, 
   const long long pairs = rows * heads;
   long long dgrid = (pairs * 8 + 255) / 256;
   if (dgrid > static_cast<long long>(sm_count()) * 16) dgrid = static_cast<long long>(sm_count()) * 16;
-  MH_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * E, st));  // (first: the kernels below chain through PDL)
+  if (zero_dq) MH_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * E, st));  // (first: the kernels below chain through PDL)
   MH_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(dgrid)), dim3(256), 0, st,
                      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T,
                      heads));

@@ -100,14 +100,20 @@ def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site
     return out, lse, keep
 
 
-def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0):
+def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0, dq_acc=None):
+    """``dq_acc``: optional fp32 [B*T, E] workspace that the caller has ALREADY zeroed (ops zeroes it on a side stream
+    under the FFN backward); without it the call zeroes a fresh one itself."""
     E = 64 * heads
     if dout.dtype != bf16 or not dout.is_contiguous() or tuple(dout.shape) != (B * T, E):
         raise ValueError("attn_bwd: dout must be contiguous bf16 [B*T, E]")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
-    dq_acc = torch.empty(B * T, E, device=qkv.device, dtype=torch.float32)
-    _call("mh_attn_bwd", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
+    fn = "mh_attn_bwd_prezeroed"
+    if dq_acc is None:
+        fn, dq_acc = "mh_attn_bwd", torch.empty(B * T, E, device=qkv.device, dtype=torch.float32)
+    elif dq_acc.dtype != torch.float32 or dq_acc.numel() != B * T * E or not dq_acc.is_contiguous():
+        raise ValueError("attn_bwd: dq_acc must be a contiguous fp32 workspace of B*T*E elements")
+    _call(fn, _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
           c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), _s())
     return dqkv
 

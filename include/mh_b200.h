@@ -48,7 +48,11 @@ enum {
   MH_EPI_RES = 2,   /* D(bf16) = dropout(acc + bias) + aux_in[m,n]                             */
   MH_EPI_F32 = 3,   /* D(f32) += acc * (mask ? mask[m,n] : 1)   (atomic; split-K capable)      */
   MH_EPI_DGELU = 4, /* D(bf16) = acc * dropout_keep_scale * gelu'(aux_in[m,n])                 */
-  MH_EPI_ADD = 5    /* D(bf16) = acc + aux_in[m,n]                                             */
+  MH_EPI_ADD = 5,   /* D(bf16) = acc + aux_in[m,n]                                             */
+  MH_EPI_DELTA = 6  /* D(bf16) = acc; delta[m / T, n / 64, m % T] = sum over the 64 columns of a head of
+                       bf16(acc)[m,n] * aux_in[m,n] -- the rowsum(dO * O) term of the attention backward
+                       (pytorch_code/forward_multihead_attention.py:62, softmax backward), fused into the
+                       out_proj dgrad GEMM that produces dO.  K-major A, MN-major B, 256-wide tiles only. */
 };
 
 typedef struct {
@@ -65,6 +69,8 @@ typedef struct {
   float p_drop; uint64_t seed; uint32_t site;   /* dropout stream (see mh_common.cuh) */
   int block_n;               /* 0 = auto; 128 / 256 = single-CTA 128 x block_n tiles; -256 = CTA-pair (cta_group::2) 256 x 256 tiles */
   int split_k;               /* 0 = auto (MH_EPI_F32 only), else number of K splits */
+  float* delta;              /* MH_EPI_DELTA: f32 [M / delta_T, N / 64, delta_T], else ignored */
+  int delta_T;               /* MH_EPI_DELTA: rows per batch element (frames); M %% delta_T == 0 */
 } mh_gemm_args;
 
 int mh_gemm(const mh_gemm_args* args, void* stream);
@@ -89,11 +95,12 @@ int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, uint8
 int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                 const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
                 float p_drop, uint64_t seed, uint32_t site, void* stream);
-/* mh_attn_bwd zeroes dq_acc itself; the _prezeroed variant expects the caller to have done so (e.g. on a side stream,
- * overlapped with the GEMMs in front of it). */
-int mh_attn_bwd_prezeroed(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
-                const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
-                float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* mh_attn_bwd_ex: flags & 1 = dq_acc has already been zeroed by the caller (e.g. on a side stream, overlapped with the
+ * GEMMs in front of the call); flags & 2 = delta already holds rowsum(dO * O) per (batch, head, query) -- written by the
+ * MH_EPI_DELTA epilogue of the out_proj dgrad GEMM that produced dout. */
+int mh_attn_bwd_ex(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                   const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
+                   float p_drop, uint64_t seed, uint32_t site, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNorm family (module.py:121-123,129-131,232-236: dropout -> +residual -> LayerNorm is

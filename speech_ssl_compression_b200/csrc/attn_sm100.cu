@@ -1014,26 +1014,27 @@ extern "C" int mh_attn_trace_read(long long* host_out) {  // debug builds only: 
 
 static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                          const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, void* stream);
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, void* stream);
 
 extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                            const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
                            int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
   return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site, true,
-                       stream);
+                       false, stream);
 }
 
-// same, for a dq_acc workspace the caller has ALREADY zeroed (e.g. on a side stream under the preceding GEMMs)
-extern "C" int mh_attn_bwd_prezeroed(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
-                                     const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                                     int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
-  return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site, false,
-                       stream);
+// flags: 1 = dq_acc has ALREADY been zeroed by the caller (e.g. on a side stream under the preceding GEMMs),
+//        2 = delta already holds rowsum(dO * O) (the MH_EPI_DELTA epilogue of the GEMM that produced dO)
+extern "C" int mh_attn_bwd_ex(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                              const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
+                              int causal, float p_drop, uint64_t seed, uint32_t site, int flags, void* stream) {
+  return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site,
+                       !(flags & 1), (flags & 2) != 0, stream);
 }
 
 static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                          const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, void* stream) {
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, void* stream) {
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_bwd: bad shape B=%d T=%d heads=%d", B, T, heads);
   MH_CHECK(!(p_drop > 0.f) || keep_bits != nullptr, "attn_bwd: dropout needs the keep bits written by mh_attn_fwd");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1059,10 +1060,12 @@ static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, co
   long long dgrid = (pairs * 8 + 255) / 256;
   if (dgrid > static_cast<long long>(sm_count()) * 16) dgrid = static_cast<long long>(sm_count()) * 16;
   if (zero_dq) MH_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * E, st));  // (first: the kernels below chain through PDL)
-  MH_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(dgrid)), dim3(256), 0, st,
-                     reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T,
-                     heads));
-  ++g_launches;
+  if (!have_delta) {
+    MH_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(dgrid)), dim3(256), 0, st,
+                       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, T,
+                       heads));
+    ++g_launches;
+  }
   AttnBwdParams p;
   p.kv_len = kv_len; p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);

@@ -26,6 +26,10 @@
 #include "mh_common.cuh"
 #include "mh_ptx.cuh"
 
+#ifndef MH_EPI_KO
+#define MH_EPI_KO 0  // timing experiments only (wrong results): 1 no TMA-store read waits, 2 no GELU / dGELU / dropout math
+#endif
+
 namespace mh {
 
 constexpr int BM = 128;
@@ -55,6 +59,8 @@ struct GemmDev {
   const uint8_t* mask;
   DropCfg drop;
   int split_k;
+  float* delta;   // MH_EPI_DELTA: f32 [M / delta_T, N / 64, delta_T]
+  int delta_T;
 };
 
 // byte offset of 16-byte chunk `ch` of row `r` in a staging tile whose rows are ROWB bytes, laid out the
@@ -86,7 +92,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
                                               int n0, bool has_k, uint64_t* tfull_bar, uint32_t acc_phase, uint64_t* aux_bar,
                                               uint32_t& aux_phase, uint32_t tempty_cluster_addr) {
   constexpr bool OUT_F32 = EPI == MH_EPI_F32;
-  constexpr bool HAS_AUX_IN = EPI == MH_EPI_RES || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD;
+  constexpr bool HAS_AUX_IN = EPI == MH_EPI_RES || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_DELTA;
   constexpr int CG = BN / EPI_GROUPS;                    // columns per epilogue group
   constexpr int SUBC = OUT_F32 ? 32 : CG;                // columns staged per pass (a staging row is <= 128 bytes)
   constexpr int ROWB = SUBC * (OUT_F32 ? 4 : 2);         // staging row bytes
@@ -99,7 +105,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   // (1) the staging tile is free once the previous TMA store has read it; residual / pre-activation
   //     tiles are fetched into it right away so the load overlaps the wait for the accumulator
   if (e.leader) {
-    bulk_wait_read0();
+    if (!(MH_EPI_KO & 1)) bulk_wait_read0();
     if (HAS_AUX_IN && active) {
       mbar_expect_tx(aux_bar, 128 * ROWB);
       tma_load_2d(stg, tmAuxIn, aux_bar, gcol0, m0);
@@ -176,6 +182,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   const uint32_t stg_s = smem_u32(stg);
   const float drop_s = (EPI == MH_EPI_GELU && p.drop.thresh != 0) ? p.drop.scale : 1.f;
   const float drop_lg = (EPI == MH_EPI_GELU && p.drop.thresh != 0) ? log2f(p.drop.scale) : 0.f;
+  float dsum = 0.f;  // MH_EPI_DELTA: this row's dot product over the group's 64 columns (= one attention head)
   if (active) {
     auto sub_chunk = [&](int s) {
       const int col_in_tile = e.grp * CG + s * 32;
@@ -184,7 +191,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       uint32_t r[32];
       tmem_ld32(tmem_acc + e.lane_off + col_in_tile, r);
       uint32_t kw = 0xffffffffu;
-      if (HAS_DROP && p.drop.thresh != 0) kw = dstate.keep32(p.drop, drop_base + (col_in_tile >> 5));
+      if (HAS_DROP && p.drop.thresh != 0 && !(MH_EPI_KO & 2)) kw = dstate.keep32(p.drop, drop_base + (col_in_tile >> 5));
       tmem_ld_wait();
       uint4 o4[4];
 #pragma unroll
@@ -213,12 +220,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           const uint4 pre = f32_to_bf16x8(v);
           if (p.has_aux_out) sts128(slot_s, pre);
           bf16x8_to_f32(pre, v);
-          gelu_erf8(v, drop_s, drop_lg);  // (the dropout keep-scale rides along in the exponent: no multiply later)
+          if (!(MH_EPI_KO & 2)) gelu_erf8(v, drop_s, drop_lg);  // (the dropout keep-scale rides along in the exponent: no multiply later)
         }
         if (EPI == MH_EPI_DGELU) {
           float pre[8];
           bf16x8_to_f32(lds128_plain(slot_s), pre);
-          gelu_erf_grad_mul8(v, pre);
+          if (!(MH_EPI_KO & 2)) gelu_erf_grad_mul8(v, pre);
         }
         if (HAS_DROP) {
           if (p.drop.thresh != 0) {
@@ -237,6 +244,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           for (int j = 0; j < 4; ++j) unpack2f(fadd2(pack2f(v[2 * j], v[2 * j + 1]), pack2f(a[2 * j], a[2 * j + 1])), v[2 * j], v[2 * j + 1]);
         }
         o4[q] = f32_to_bf16x8(v);
+        if (EPI == MH_EPI_DELTA) {
+          // delta = rowsum(dO * O) per head (the softmax-backward correction term of the attention backward): dO is this
+          // GEMM's (rounded) output, the O tile was prefetched into the staging tile like a residual
+          float g[8], o[8];
+          bf16x8_to_f32(o4[q], g);
+          bf16x8_to_f32(lds128_plain(slot_s), o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dsum = fmaf(g[j], o[j], dsum);
+        }
         if (!(EPI == MH_EPI_GELU && p.has_aux_out)) sts128(slot_s, o4[q]);
       }
       if (EPI == MH_EPI_GELU && p.has_aux_out) {
@@ -259,6 +275,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       for (int s = 0; s < CG / 32; ++s) sub_chunk(s);
     }
   }
+  if (EPI == MH_EPI_DELTA && active && row < p.M) {
+    static_assert(EPI != MH_EPI_DELTA || CG == 64, "the delta epilogue needs 64-column groups (one head each): BN = 256");
+    const long long b = row / p.delta_T, t = row - b * p.delta_T;
+    p.delta[(b * (p.N >> 6) + (gcol0 >> 6)) * p.delta_T + t] = dsum;
+  }
   // (3) TMEM buffer back to the MMA warp
   tc_fence_before();
   __syncwarp();
@@ -272,7 +293,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       if (e.leader) {
         tma_store_2d(tmAuxOut, stg, gcol0, m0);
         bulk_commit();
-        bulk_wait_read0();
+        if (!(MH_EPI_KO & 1)) bulk_wait_read0();
       }
       bar_sync(e.bar_id, 128);
 #pragma unroll
@@ -738,7 +759,7 @@ static int launch_pair(const GemmMaps& t, const GemmDev& d, int grid, cudaStream
 template <int EPI>
 static int dispatch_major_pair(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
   if (!a->a_mn && !a->b_mn) return launch_pair<EPI, false, false>(t, d, grid, st);
-  if constexpr (EPI == MH_EPI_BF16 || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_F32) {
+  if constexpr (EPI == MH_EPI_BF16 || EPI == MH_EPI_DGELU || EPI == MH_EPI_ADD || EPI == MH_EPI_F32 || EPI == MH_EPI_DELTA) {
     if (!a->a_mn && a->b_mn) return launch_pair<EPI, false, true>(t, d, grid, st);
   }
   if constexpr (EPI == MH_EPI_F32 || EPI == MH_EPI_BF16) {
@@ -757,6 +778,7 @@ static int dispatch_epi_pair(const mh_gemm_args* a, const GemmMaps& t, const Gem
     case MH_EPI_F32: return dispatch_major_pair<MH_EPI_F32>(a, t, d, grid, st);
     case MH_EPI_DGELU: return dispatch_major_pair<MH_EPI_DGELU>(a, t, d, grid, st);
     case MH_EPI_ADD: return dispatch_major_pair<MH_EPI_ADD>(a, t, d, grid, st);
+    case MH_EPI_DELTA: return dispatch_major_pair<MH_EPI_DELTA>(a, t, d, grid, st);
   }
   set_error("unknown epilogue %d", a->epilogue);
   return 1;
@@ -766,6 +788,12 @@ template <int BN, int EPI>
 static int dispatch_major(const mh_gemm_args* a, const GemmMaps& t, const GemmDev& d, int grid, cudaStream_t st) {
   if constexpr (EPI == MH_EPI_F32 && BN != 128) {
     set_error("fp32 accumulate epilogue is built for block_n = 128 only");
+    return 1;
+  } else if constexpr (EPI == MH_EPI_DELTA) {
+    if constexpr (BN == 256) {
+      if (!a->a_mn && a->b_mn) return launch<BN, EPI, false, true>(t, d, grid, st);
+    }
+    set_error("the delta epilogue is built for block_n = 256, a K-major, b MN-major only");
     return 1;
   } else {
     if (!a->a_mn && !a->b_mn) return launch<BN, EPI, false, false>(t, d, grid, st);
@@ -792,6 +820,7 @@ static int dispatch_epi(const mh_gemm_args* a, const GemmMaps& t, const GemmDev&
     case MH_EPI_F32: return dispatch_major<BN, MH_EPI_F32>(a, t, d, grid, st);
     case MH_EPI_DGELU: return dispatch_major<BN, MH_EPI_DGELU>(a, t, d, grid, st);
     case MH_EPI_ADD: return dispatch_major<BN, MH_EPI_ADD>(a, t, d, grid, st);
+    case MH_EPI_DELTA: return dispatch_major<BN, MH_EPI_DELTA>(a, t, d, grid, st);
   }
   set_error("unknown epilogue %d", a->epilogue);
   return 1;
@@ -805,8 +834,11 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   MH_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "bad GEMM shape %d x %d x %d", a->M, a->N, a->K);
   MH_CHECK(a->N % 8 == 0, "N must be a multiple of 8 (got %d)", a->N);
   MH_CHECK(a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, "D must be 16-byte aligned, ldd %% 8 == 0");
-  if (a->epilogue == MH_EPI_RES || a->epilogue == MH_EPI_DGELU || a->epilogue == MH_EPI_ADD)
+  if (a->epilogue == MH_EPI_RES || a->epilogue == MH_EPI_DGELU || a->epilogue == MH_EPI_ADD || a->epilogue == MH_EPI_DELTA)
     MH_CHECK(a->aux_in != nullptr && a->ld_aux % 8 == 0, "epilogue %d needs aux_in", a->epilogue);
+  if (a->epilogue == MH_EPI_DELTA)
+    MH_CHECK(a->delta != nullptr && a->delta_T > 0 && a->M % a->delta_T == 0 && a->N % 64 == 0 && !a->a_mn && a->b_mn,
+             "delta epilogue: needs delta, delta_T dividing M, N %% 64 == 0, a K-major and b MN-major");
   if (a->epilogue == MH_EPI_GELU && a->aux_out != nullptr) MH_CHECK(a->ld_aux % 8 == 0, "ld_aux %% 8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -833,6 +865,7 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
       bn = 128;
     }
     if (bn == 0) bn = (a->N >= 256 && num_m * ((a->N + 255) / 256) >= sms) ? 256 : 128;
+    if (a->epilogue == MH_EPI_DELTA) bn = 256;  // 64-column epilogue groups = one attention head each
     MH_CHECK(bn == 128 || bn == 256, "block_n must be 0, 128, 256 or -256");
   } else {
     bn = G2_BN;
@@ -889,6 +922,8 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   d.drop = make_drop(a->p_drop, a->seed, a->site);
   MH_CHECK(d.drop.thresh == 0 || a->N % 32 == 0, "gemm: a dropout epilogue needs N %% 32 == 0 (one dropout stream word = 32 columns), got N=%d", a->N);
   d.split_k = splits;
+  d.delta = a->epilogue == MH_EPI_DELTA ? a->delta : nullptr;
+  d.delta_T = a->epilogue == MH_EPI_DELTA ? a->delta_T : 1;
   const int tiles = tiles_m * num_n * splits;
   if (pair) return dispatch_epi_pair(a, t, d, 2 * (tiles < units ? tiles : units), st);
   const int grid = tiles < sms ? tiles : sms;

@@ -9,7 +9,7 @@ from ctypes import byref, c_float, c_int, c_longlong, c_uint32, c_uint64, c_void
 import torch
 
 from . import lib as L
-from .lib import EPI_ADD, EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RES  # noqa: F401
+from .lib import EPI_ADD, EPI_BF16, EPI_DELTA, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RES  # noqa: F401
 
 bf16 = torch.bfloat16
 
@@ -30,7 +30,7 @@ def _chk2d(t, name, dtype=None):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None, aux_in=None, aux_out=None,
-         mask=None, p_drop=0.0, seed=0, site=0, block_n=0, split_k=0):
+         mask=None, p_drop=0.0, seed=0, site=0, block_n=0, split_k=0, delta=None, delta_T=0):
     """out[M,N] (op)= A[M,K] @ B[N,K]^T.  ``a``: [M,K] (or [K,M] when a_mn), ``b``: [N,K] (or
     [K,N] when b_mn); bf16, unit inner stride.  ``out`` bf16 (or fp32 for EPI_F32, accumulated)."""
     _chk2d(a, "a", bf16)
@@ -71,6 +71,11 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None, aux
         args.mask = mask.data_ptr()
     args.p_drop, args.seed, args.site = float(p_drop), int(seed), int(site)
     args.block_n, args.split_k = block_n, split_k
+    if epilogue == EPI_DELTA:
+        if delta is None or delta.dtype != torch.float32 or not delta.is_contiguous() or delta_T <= 0 or M % delta_T \
+                or N % 64 or delta.numel() != M * (N // 64):
+            raise ValueError("gemm: EPI_DELTA needs delta fp32 [M / T, N / 64, T] and delta_T dividing M")
+        args.delta, args.delta_T = delta.data_ptr(), int(delta_T)
     L.check(L.lib().mh_gemm(byref(args), _s()), "mh_gemm")
     return out
 
@@ -100,21 +105,30 @@ def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site
     return out, lse, keep
 
 
-def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0, dq_acc=None):
+def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0, dq_acc=None,
+             delta=None):
     """``dq_acc``: optional fp32 [B*T, E] workspace that the caller has ALREADY zeroed (ops zeroes it on a side stream
-    under the FFN backward); without it the call zeroes a fresh one itself."""
+    under the FFN backward); without it the call zeroes a fresh one itself.  ``delta``: optional precomputed
+    rowsum(dO * O) [B, heads, T] (the out_proj dgrad GEMM's EPI_DELTA epilogue); without it a kernel computes it."""
     E = 64 * heads
     if dout.dtype != bf16 or not dout.is_contiguous() or tuple(dout.shape) != (B * T, E):
         raise ValueError("attn_bwd: dout must be contiguous bf16 [B*T, E]")
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
-    fn = "mh_attn_bwd_prezeroed"
+    flags = 0
+    if delta is None:
+        delta = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32)
+    else:
+        if delta.dtype != torch.float32 or delta.numel() != B * heads * T or not delta.is_contiguous():
+            raise ValueError("attn_bwd: delta must be contiguous fp32 [B, heads, T]")
+        flags |= 2
     if dq_acc is None:
-        fn, dq_acc = "mh_attn_bwd", torch.empty(B * T, E, device=qkv.device, dtype=torch.float32)
-    elif dq_acc.dtype != torch.float32 or dq_acc.numel() != B * T * E or not dq_acc.is_contiguous():
-        raise ValueError("attn_bwd: dq_acc must be a contiguous fp32 workspace of B*T*E elements")
-    _call(fn, _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
-          c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), _s())
+        dq_acc = torch.empty(B * T, E, device=qkv.device, dtype=torch.float32)
+    else:
+        if dq_acc.dtype != torch.float32 or dq_acc.numel() != B * T * E or not dq_acc.is_contiguous():
+            raise ValueError("attn_bwd: dq_acc must be a contiguous fp32 workspace of B*T*E elements")
+        flags |= 1
+    _call("mh_attn_bwd_ex", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
+          c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), c_int(flags), _s())
     return dqkv
 
 

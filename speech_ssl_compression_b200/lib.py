@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_uint32, c_uint64, c_v
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MH_B200_LIB") or os.path.join(_HERE, "libmh_b200.so")  # override: A/B builds of the same ABI
 
-EPI_BF16, EPI_GELU, EPI_RES, EPI_F32, EPI_DGELU, EPI_ADD = range(6)
+EPI_BF16, EPI_GELU, EPI_RES, EPI_F32, EPI_DGELU, EPI_ADD, EPI_DELTA = range(7)
 
 
 class GemmArgs(ctypes.Structure):
@@ -28,6 +28,8 @@ class GemmArgs(ctypes.Structure):
         ("p_drop", c_float), ("seed", c_uint64), ("site", c_uint32),
         ("block_n", c_int),
         ("split_k", c_int),
+        ("delta", c_void_p),
+        ("delta_T", c_int),
     ]
 
 

@@ -421,10 +421,12 @@ class EncoderLayerFn(torch.autograd.Function):
         # ---- attention block ----
         _wgrad(dz1, ctxv, mha.out_proj)
         dctx = torch.empty_like(ctxv)
-        K.gemm(dz1, wo, dctx, b_mn=True)
+        # out_proj dgrad; its epilogue also emits delta = rowsum(dO * O) per head (64-column epilogue groups = heads)
+        delta = torch.empty(B, heads, T, device=dctx.device, dtype=torch.float32)
+        K.gemm(dz1, wo, dctx, b_mn=True, epilogue=K.EPI_DELTA, aux_in=ctxv, delta=delta, delta_T=T)
         torch.cuda.current_stream().wait_event(zero_done)
         dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, keep, B, T, heads, causal=causal, p_drop=p_att, seed=seed,
-                          site=site_base + SITE_ATTN, dq_acc=dq_acc)
+                          site=site_base + SITE_ATTN, dq_acc=dq_acc, delta=delta)
         _wgrad_qkv(dqkv, a_in, mha, E)
         dx = None
         if ctx.needs_input_grad[0]:

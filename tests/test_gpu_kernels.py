@@ -116,6 +116,33 @@ def test_gemm_epilogues_gelu_res_dgelu_add():
     assert rel(out, (acc - bias) * x.grad) < 6e-3
 
 
+@pytest.mark.parametrize("B,T,H,block_n", [(32, 750, 12, 0), (2, 300, 3, 0), (4, 192, 7, 256)])
+def test_gemm_delta_epilogue_feeds_the_attention_backward(B, T, H, block_n):
+    """MH_EPI_DELTA: the out_proj dgrad GEMM also emits delta = rowsum(dO * O) per (batch, head, query) -- same values
+    as the stand-alone kernel inside mh_attn_bwd, and the attention backward gives the same gradients with it."""
+    k = K()
+    E = 64 * H
+    M = B * T
+    torch.manual_seed(3)
+    dz = (torch.randn(M, 768, device=DEV) * 0.5).to(bf16)
+    wo = (torch.randn(768, E, device=DEV) * 0.03).to(bf16)        # forward weight [out, in]: MN-major B of the dgrad
+    qkv = torch.randn(M, 3 * E, device=DEV).to(bf16)
+    lens_t = torch.tensor([T - 7 * (i % 3) for i in range(B)], device=DEV, dtype=torch.int32)
+    ctx, lse, keep = k.attn_fwd(qkv, lens_t, B, T, H, p_drop=0.1, seed=5, site=1)
+    dctx, dref = torch.empty(M, E, device=DEV, dtype=bf16), torch.empty(M, E, device=DEV, dtype=bf16)
+    delta = torch.full((B, H, T), float("nan"), device=DEV)
+    k.gemm(dz, wo, dctx, b_mn=True, epilogue=k.EPI_DELTA, aux_in=ctx, delta=delta, delta_T=T, block_n=block_n)
+    k.gemm(dz, wo, dref, b_mn=True)
+    assert torch.equal(dctx, dref)
+    want = (dref.float() * ctx.float()).view(B, T, H, 64).sum(-1).permute(0, 2, 1)
+    torch.testing.assert_close(delta, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+    g_fused = k.attn_bwd(qkv, lens_t, ctx, dctx, lse, keep, B, T, H, p_drop=0.1, seed=5, site=1, delta=delta)
+    g_plain = k.attn_bwd(qkv, lens_t, ctx, dctx, lse, keep, B, T, H, p_drop=0.1, seed=5, site=1)
+    assert rel(g_fused, g_plain) < 2e-3  # (fp32 reduce-add order differs from launch to launch)
+    with pytest.raises(RuntimeError):
+        k.gemm(dz, wo.t().contiguous(), dctx, epilogue=k.EPI_DELTA, aux_in=ctx, delta=delta, delta_T=T)  # K-major B: not built
+
+
 def test_gemm_dropout_epilogue_statistics_and_regeneration():
     """Dropout in the epilogue: keep-rate ~ 1-p, survivors scaled by 1/(1-p), the same
     (seed, site) regenerates the same mask, a different site gives a different one, and

@@ -237,7 +237,8 @@ def live_rooflines(run_once, peaks, B, T):
     from speech_ssl_compression_b200 import kernels as K
 
     names = {K.EPI_BF16: "bias", K.EPI_GELU: "bias+GELU+dropout", K.EPI_RES: "bias+dropout+residual",
-             K.EPI_F32: "wgrad fp32 reduce-add", K.EPI_DGELU: "dGELU+dropout", K.EPI_ADD: "+residual grad"}
+             K.EPI_F32: "wgrad fp32 reduce-add", K.EPI_DGELU: "dGELU+dropout", K.EPI_ADD: "+residual grad",
+             K.EPI_DELTA: "dgrad + attention delta"}
     rec, arec = [], []
     real, real_af, real_ab = K.gemm, K.attn_fwd, K.attn_bwd
 
@@ -309,7 +310,7 @@ def live_rooflines(run_once, peaks, B, T):
         flops += fl
         ms += t
         abytes += nb
-        d = by.setdefault(names[epi], [0, 0.0, 0.0])
+        d = by.setdefault(names.get(epi, f"epilogue {epi}"), [0, 0.0, 0.0])
         d[0] += 1; d[1] += fl; d[2] += t
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     burst = peaks.get("bf16_tflops", 1590.0)

@@ -122,3 +122,21 @@ def test_train_cli_distillation(tmp_path):
     train.main(["-m", "distillation", "-g", mp, "-c", rp, "-n", exp, "-i", ck, "--synthetic"])
     st = torch.load(os.path.join(exp, "last-step.ckpt"), map_location="cpu", weights_only=False)
     assert st["Step"] == 6 and not any(k.startswith("teacher") for k in st["model"])
+
+
+@pytest.mark.parametrize("extra", [[], ["--mode", "extract"], ["--mode", "row+weight", "--accum", "2"]])
+def test_bench_prints_one_contract_line(extra):
+    """bench.py end to end on a small shape: one JSON line with the keys the measurement contract names."""
+    import json
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--batch", "2", "--frames", "256",
+           "--no-cpu-baseline", "--no-gpu-baseline"] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "roofline_attention"):
+        assert key in d, key
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert 0 < d["roofline"]["frac"] < 1.2 and d["config"]["workload"].split(":")[0] in ("cfg2", "cfg4", "extraction")

@@ -590,3 +590,50 @@ def test_train_step_gradient_accumulation():
         assert int(ts.opt.step_count) == 3
     assert len(traj[True]) == 3 and traj[True][2] < traj[True][0]
     np.testing.assert_allclose(traj[True], traj[False], rtol=2e-2)
+
+
+def test_weight_pruning_keeps_training_after_prune_api():
+    """after ``WeightPruningTools.prune_api`` (remove -> global_unstructured) every prunable
+    parameter must still BE its slot of the flat buffer the fused optimizer updates, keep training, and the effective
+    operands (bf16 shadow / fp32 bias copy written by the masked Adam kernel) must equal param * mask."""
+    from speech_ssl_compression_b200.trainer import TrainStep
+    from speech_ssl_compression_b200.upstream.melhubert.pretrain_expert import MelHuBERTPretrainer
+    from speech_ssl_compression_b200.weight_pruning.wp_utils import WeightPruningTools
+
+    cfg = base_cfg(20, 2)
+    B, T, D = 2, 256, 80
+    torch.manual_seed(5)
+    ex = MelHuBERTPretrainer({"melhubert": dict(cfg)}, None, DEV, False).to(DEV).train()
+    rc = {"runner": {}, "prune": {"pruning_condition": "fixed", "strategy": "L1Unstructured", "n_iters": 2, "warnup": 1,
+                                  "period": 1, "sparsity": [0.3, 0.5]}}
+    tools = WeightPruningTools(Namespace(expdir=tempfile.mkdtemp(), device=DEV), rc, {"melhubert": cfg}, ex, None)
+    ts = TrainStep(ex, B, T, D, lr=1e-3, max_norm=10.0, use_graph=True)
+    f, l, p = O.synth_batch(B, T, D, [256, 200], seed=8)
+    batch = (f.pin_memory(), l.pin_memory(), p.pin_memory(), [256, 200])
+    np.random.seed(1)
+    for amount in (0.3, 0.5):
+        tools.prune_api(ts.opt, 0, 10)
+        ts.graphs = None  # (what runner.py does after a weight-pruning event)
+        fc1 = ex.model.encoder.layers[0].fc1
+        w, m = fc1.weight_orig, fc1.weight_mask
+        o = w._mh_flat[1]
+        assert w.data_ptr() == ts.flat.flat_param.data_ptr() + 4 * o          # still the optimizer's storage
+        assert abs(float((~m).float().mean()) - amount) < 2e-2
+        before = w.detach().clone()
+        for _ in range(2):
+            ts.load_batch(*batch)
+            ts.run()
+        torch.cuda.synchronize()
+        assert np.isfinite(ts.read_loss())
+        assert float((w.detach() - before).abs().max()) > 0                    # it trains
+        n = w.numel()
+        shadow = ts.flat.flat_bf16[o:o + n].view_as(w).float()
+        want = (w.detach() * m).to(torch.bfloat16).float()
+        assert torch.equal(shadow, want)                                       # operands = param * mask
+        assert torch.equal(ts.flat.flat_mask[o:o + n].view_as(m).bool(), m)
+        b, bm = fc1.bias_orig, fc1.bias_mask
+        ob = b._mh_flat[1]
+        assert torch.equal(ts.flat.flat_eff[ob:ob + b.numel()], b.detach() * bm)
+        # pruned elements received no update from the masked optimizer step (their gradient is dropped, moments were 0)
+        if amount == 0.3:
+            assert torch.equal(w.detach()[~m], before[~m])

@@ -98,6 +98,10 @@ int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void*
 /* mh_attn_bwd_ex: flags & 1 = dq_acc has already been zeroed by the caller (e.g. on a side stream, overlapped with the
  * GEMMs in front of the call); flags & 2 = delta already holds rowsum(dO * O) per (batch, head, query) -- written by the
  * MH_EPI_DELTA epilogue of the out_proj dgrad GEMM that produced dout. */
+/* flags & 4 = leave dQ in the fp32 workspace; the caller finishes with mh_dq_finish_colsum, which writes
+ * dqkv[:, 0:E] = bf16(dq_acc) AND accumulates colsum[c] += sum over rows of dqkv[:, c] for all 3E columns (the q / k / v
+ * bias gradients, fairseq_code/multihead_attention.py:151) in one pass. */
+int mh_dq_finish_colsum(const float* dq_acc, void* dqkv, float* colsum, int rows, int E, void* stream);
 int mh_attn_bwd_ex(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                    const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
                    float p_drop, uint64_t seed, uint32_t site, int flags, void* stream);
@@ -117,6 +121,12 @@ int mh_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
  * dgamma / dbeta (f32 [cols]) are accumulated (atomicAdd). */
 int mh_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                      void* dx, void* dx_drop, float* dgamma, float* dbeta, int rows, int cols, float p_in,
+                     uint64_t seed_in, uint32_t site_in, float p_out, uint64_t seed_out, uint32_t site_out,
+                     void* stream);
+/* same, and dcol[c] += sum over rows of the output (dx_drop when given, else dx): the bias gradient of the linear layer
+ * whose (dropped) output fed this LayerNorm's input -- saves the separate column-sum pass over that tensor */
+int mh_layernorm_bwd_colsum(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dcol, int rows, int cols, float p_in,
                      uint64_t seed_in, uint32_t site_in, float p_out, uint64_t seed_out, uint32_t site_out,
                      void* stream);
 

@@ -969,9 +969,102 @@ __global__ void dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat16* __
            make_uint4(f32x2_to_bf16(a.x, a.y), f32x2_to_bf16(a.z, a.w), f32x2_to_bf16(bb.x, bb.y), f32x2_to_bf16(bb.z, bb.w)));
   }
 }
+
+// dq_finish + the q / k / v bias gradients in one pass: dqkv[:, 0:E] = bf16(dq_acc) and out[c] += sum over rows of
+// dqkv[:, c] for all 3E columns (the dQ columns are summed as rounded, like the separate column-sum kernel would see them).
+// Block = 8 warps over a slab of 256 columns and a slice of rows (the layout of norm.cu's colsum_kernel).
+__global__ void __launch_bounds__(256)
+dq_finish_colsum_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ out, int rows, int E,
+                        int rows_per_block) {
+  pdl_prologue();
+  __shared__ float red[8][32 * 8 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = blockIdx.x * 256 + lane * 8;
+  const int cols = 3 * E;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col0 < cols) {
+    if (col0 < E) {
+      for (int r = r0 + warp; r < r1; r += 32) {  // four rows (8 x 16-byte loads) in flight per lane
+        float4 a[4], b4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ru = r + 8 * u;
+          if (ru < r1) {
+            const float* pu = dq + static_cast<long long>(ru) * E + col0;
+            a[u] = __ldg(reinterpret_cast<const float4*>(pu));
+            b4[u] = __ldg(reinterpret_cast<const float4*>(pu + 4));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ru = r + 8 * u;
+          if (ru < r1) {
+            const uint4 o = make_uint4(f32x2_to_bf16(a[u].x, a[u].y), f32x2_to_bf16(a[u].z, a[u].w),
+                                       f32x2_to_bf16(b4[u].x, b4[u].y), f32x2_to_bf16(b4[u].z, b4[u].w));
+            stg128(dqkv + static_cast<long long>(ru) * cols + col0, o);
+            float v[8];
+            bf16x8_to_f32(o, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+          }
+        }
+      }
+    } else {
+      const __nv_bfloat16* xp = dqkv + col0;
+      int r = r0 + warp;
+      for (; r + 24 < r1; r += 32) {
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = ldg128(xp + static_cast<long long>(r + 8 * u) * cols);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float v[8];
+          bf16x8_to_f32(q[u], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+      }
+      for (; r < r1; r += 8) {
+        float v[8];
+        bf16x8_to_f32(ldg128(xp + static_cast<long long>(r) * cols), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
 }  // namespace mh
 
 using namespace mh;
+
+// dqkv[:, 0:E] = bf16(dq_acc) and colsum[c] += sum_rows dqkv[:, c] (c < 3E): finishes an mh_attn_bwd_ex call made with
+// flags & 4 and produces the q / k / v bias gradients in the same pass
+extern "C" int mh_dq_finish_colsum(const float* dq_acc, void* dqkv, float* colsum, int rows, int E, void* stream) {
+  MH_CHECK(rows > 0 && E > 0 && E % 8 == 0 && dq_acc != nullptr && dqkv != nullptr && colsum != nullptr,
+           "dq_finish_colsum: bad arguments (rows %d, E %d)", rows, E);
+  const int cols = 3 * E;
+  const int gx = (cols + 255) / 256;
+  int gy = (sm_count() * 4 + gx - 1) / gx;
+  int rpb = (rows + gy - 1) / gy;
+  if (rpb < 64) rpb = 64;
+  gy = (rows + rpb - 1) / rpb;
+  MH_CUDA(launch_pdl(dq_finish_colsum_kernel, dim3(gx, gy), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), dq_acc,
+                     reinterpret_cast<__nv_bfloat16*>(dqkv), colsum, rows, E, rpb));
+  ++g_launches;
+  return 0;
+}
 
 extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float* lse, uint8_t* keep_bits, int B, int T,
                            int heads, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
@@ -1014,27 +1107,28 @@ extern "C" int mh_attn_trace_read(long long* host_out) {  // debug builds only: 
 
 static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                          const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, void* stream);
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, bool finish, void* stream);
 
 extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                            const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
                            int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
   return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site, true,
-                       false, stream);
+                       false, true, stream);
 }
 
 // flags: 1 = dq_acc has ALREADY been zeroed by the caller (e.g. on a side stream under the preceding GEMMs),
 //        2 = delta already holds rowsum(dO * O) (the MH_EPI_DELTA epilogue of the GEMM that produced dO)
+//        4 = leave dQ in the fp32 workspace: the caller finishes with mh_dq_finish_colsum (bf16 conversion + bias gradients)
 extern "C" int mh_attn_bwd_ex(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                               const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
                               int causal, float p_drop, uint64_t seed, uint32_t site, int flags, void* stream) {
   return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site,
-                       !(flags & 1), (flags & 2) != 0, stream);
+                       !(flags & 1), (flags & 2) != 0, !(flags & 4), stream);
 }
 
 static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                          const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, void* stream) {
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, bool finish, void* stream) {
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_bwd: bad shape B=%d T=%d heads=%d", B, T, heads);
   MH_CHECK(!(p_drop > 0.f) || keep_bits != nullptr, "attn_bwd: dropout needs the keep bits written by mh_attn_fwd");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1083,6 +1177,7 @@ static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, co
   }
   MH_LAUNCH_CHECK();
   ++g_launches;
+  if (!finish) return 0;
   long long g = (rows * (E / 8) + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (g > cap) g = cap;

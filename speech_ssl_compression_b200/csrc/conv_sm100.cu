@@ -316,9 +316,19 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // weight norm (module.py:187: nn.utils.weight_norm(conv, dim=2)): w[:, :, k] = g[k] * v[:, :, k] / ||v[:, :, k]||
 // ------------------------------------------------------------------------------------------------
 __global__ void pc_normsq_kernel(const float* __restrict__ v, float* __restrict__ normsq, int rows /* C * 48 */) {
+  // (one dependent 4-byte load per trip made these three helpers pure load latency -- 60 us each for 19 MB; eight
+  //  independent rows per trip now)
   const int k = threadIdx.x;  // 128 taps
   float s = 0.f;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  int r = blockIdx.x;
+  for (; r + 7 * static_cast<int>(gridDim.x) < rows; r += 8 * gridDim.x) {
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __ldg(v + static_cast<size_t>(r + u * gridDim.x) * PC_TAPS + k);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = fmaf(x[u], x[u], s);
+  }
+  for (; r < rows; r += gridDim.x) {
     const float x = v[static_cast<size_t>(r) * PC_TAPS + k];
     s += x * x;
   }
@@ -351,7 +361,19 @@ __global__ void pc_weight_prep_kernel(const float* __restrict__ v, const float* 
 __global__ void pc_wn_dot_kernel(const float* __restrict__ dw, const float* __restrict__ v, float* __restrict__ dot, int rows) {
   const int k = threadIdx.x;
   float s = 0.f;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  int r = blockIdx.x;
+  for (; r + 7 * static_cast<int>(gridDim.x) < rows; r += 8 * gridDim.x) {
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t i = static_cast<size_t>(r + u * gridDim.x) * PC_TAPS + k;
+      a[u] = __ldg(dw + i);
+      b[u] = __ldg(v + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = fmaf(a[u], b[u], s);
+  }
+  for (; r < rows; r += gridDim.x) {
     const size_t i = static_cast<size_t>(r) * PC_TAPS + k;
     s += dw[i] * v[i];
   }
@@ -364,7 +386,20 @@ __global__ void pc_wn_bwd_kernel(const float* __restrict__ dw, const float* __re
   const int k = threadIdx.x;
   const float n = norm[k], gk = gain[k], d = dot[k];
   const float a = gk / n, bcoef = d / (n * n);
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  int r = blockIdx.x;
+  for (; r + 7 * static_cast<int>(gridDim.x) < rows; r += 8 * gridDim.x) {
+    float x[8], y[8], z[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t i = static_cast<size_t>(r + u * gridDim.x) * PC_TAPS + k;
+      x[u] = __ldg(dw + i);
+      y[u] = __ldg(v + i);
+      z[u] = dv[i];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dv[static_cast<size_t>(r + u * gridDim.x) * PC_TAPS + k] = z[u] + a * (x[u] - y[u] * bcoef);
+  }
+  for (; r < rows; r += gridDim.x) {
     const size_t i = static_cast<size_t>(r) * PC_TAPS + k;
     dv[i] += a * (dw[i] - v[i] * bcoef);
   }

@@ -143,12 +143,14 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 #endif
 constexpr int ln_bwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * 2 * nch * 512; }
 
-template <int NCH, bool EXACT, bool HAS_DIN>
+// HAS_DCOL: also accumulate the column sums of the (dropout-applied) output into dcol -- the bias gradient of the GEMM
+// that fed this LayerNorm's input (out_proj / fc2), which otherwise costs a separate pass over the same tensor
+template <int NCH, bool EXACT, bool HAS_DIN, bool HAS_DCOL>
 __global__ void __launch_bounds__(LN_WARPS * 32, LN_BWD_MINB)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, int rows, int cols_rt, const DropCfg din, const DropCfg dout) {
+              float* __restrict__ dbeta, float* __restrict__ dcol, int rows, int cols_rt, const DropCfg din, const DropCfg dout) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t lnb_ring[];
   __shared__ float red[LN_WARPS][32 * 8 + 1];
@@ -176,11 +178,15 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     }
     cp_async_commit();  // (an empty group past the end keeps the wait_group count uniform)
   };
-  float dg[NCH][8], db[NCH][8];
+  float dg[NCH][8], db[NCH][8], dc[HAS_DCOL ? NCH : 1][8];
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < (HAS_DCOL ? NCH : 1); ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dc[i][j] = 0.f;
 
   issue(warp_global, 0);
   issue(warp_global + nwarps, 1);
@@ -250,18 +256,22 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
           if (dout.thresh != 0) DropState::apply8(dout, kout[i], o);
           stg128(dx_drop + off + i * 256, f32_to_bf16x8(o));
         }
+        if (HAS_DCOL) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dc[i][j] += o[j];
+        }
       }
     }
     stage = stage + 1 == LNB_STAGES ? 0 : stage + 1;
   }
   cp_async_wait<0>();
   // block reduction of the per-warp partial dgamma / dbeta, then one atomic per column
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (HAS_DCOL ? 3 : 2); ++pass) {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : (pass == 1 ? db[i][j] : dc[HAS_DCOL ? i : 0][j]);
       __syncthreads();
       const int c = threadIdx.x;  // 256 threads <-> 256 columns of this chunk group
       const int col = (32 * i) * 8 + c;
@@ -269,7 +279,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < LN_WARPS; ++w) t += red[w][c];
-        atomicAdd((pass == 0 ? dgamma : dbeta) + col, t);
+        atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dcol)) + col, t);
       }
     }
   }
@@ -333,9 +343,9 @@ static int launch_ln_fwd(int grid, cudaStream_t st, Args... args) {
   return 0;
 }
 
-template <int NCH, bool EXACT, bool HAS_DIN, typename... Args>
+template <int NCH, bool EXACT, bool HAS_DIN, bool HAS_DCOL, typename... Args>
 static int launch_ln_bwd(int grid, cudaStream_t st, Args... args) {
-  auto kfn = ln_bwd_kernel<NCH, EXACT, HAS_DIN>;
+  auto kfn = ln_bwd_kernel<NCH, EXACT, HAS_DIN, HAS_DCOL>;
   static bool configured = false;  // the row ring needs the > 48 KB opt-in
   if (!configured) {
     MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_bwd_smem_bytes(NCH)));
@@ -456,10 +466,9 @@ extern "C" int mh_layernorm_fwd(const void* x, const float* gamma, const float* 
   });
 }
 
-extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
-                                const float* rstd, void* dx, void* dx_drop, float* dgamma, float* dbeta, int rows,
-                                int cols, float p_in, uint64_t seed_in, uint32_t site_in, float p_out,
-                                uint64_t seed_out, uint32_t site_out, void* stream) {
+static int ln_bwd_impl(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                       void* dx_drop, float* dgamma, float* dbeta, float* dcol, int rows, int cols, float p_in,
+                       uint64_t seed_in, uint32_t site_in, float p_out, uint64_t seed_out, uint32_t site_out, void* stream) {
   MH_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm_bwd: bad shape %d x %d", rows, cols);
   MH_CHECK(!(p_in > 0.f || p_out > 0.f) || cols % 32 == 0, "layernorm_bwd: dropout needs cols %% 32 == 0, got %d", cols);
   MH_CHECK(dy != nullptr && x != nullptr && gamma != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr &&
@@ -471,16 +480,45 @@ extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamm
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_BWD_GRID_MULT);
   const DropCfg din = make_drop(p_in, seed_in, site_in), dout = make_drop(p_out, seed_out, site_out);
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+  __nv_bfloat16* ddp = reinterpret_cast<__nv_bfloat16*>(dx_drop);
   return dispatch_nch(cols, [&](auto nch, auto exact) {
     constexpr int N = decltype(nch)::value;
     constexpr bool E = decltype(exact)::value;
-    const int rc = din.thresh != 0
-                       ? launch_ln_bwd<N, E, true>(grid, st, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows, cols, din, dout)
-                       : launch_ln_bwd<N, E, false>(grid, st, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, rows, cols, din, dout);
+    int rc;
+    if (dcol != nullptr)
+      rc = din.thresh != 0
+               ? launch_ln_bwd<N, E, true, true>(grid, st, dyp, xp, gamma, mean, rstd, dxp, ddp, dgamma, dbeta, dcol, rows, cols, din, dout)
+               : launch_ln_bwd<N, E, false, true>(grid, st, dyp, xp, gamma, mean, rstd, dxp, ddp, dgamma, dbeta, dcol, rows, cols, din, dout);
+    else
+      rc = din.thresh != 0
+               ? launch_ln_bwd<N, E, true, false>(grid, st, dyp, xp, gamma, mean, rstd, dxp, ddp, dgamma, dbeta, dcol, rows, cols, din, dout)
+               : launch_ln_bwd<N, E, false, false>(grid, st, dyp, xp, gamma, mean, rstd, dxp, ddp, dgamma, dbeta, dcol, rows, cols, din, dout);
     if (rc != 0) return rc;
     ++g_launches;
     return 0;
   });
+}
+
+extern "C" int mh_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                const float* rstd, void* dx, void* dx_drop, float* dgamma, float* dbeta, int rows,
+                                int cols, float p_in, uint64_t seed_in, uint32_t site_in, float p_out,
+                                uint64_t seed_out, uint32_t site_out, void* stream) {
+  return ln_bwd_impl(dy, x, gamma, mean, rstd, dx, dx_drop, dgamma, dbeta, nullptr, rows, cols, p_in, seed_in, site_in, p_out,
+                     seed_out, site_out, stream);
+}
+
+// same, and dcol[c] += sum over rows of the output (dx_drop when given, else dx): the bias gradient of the linear layer
+// whose output fed this LayerNorm (module.py:121-123 / 129-131)
+extern "C" int mh_layernorm_bwd_colsum(const void* dy, const void* x, const float* gamma, const float* mean,
+                                       const float* rstd, void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dcol,
+                                       int rows, int cols, float p_in, uint64_t seed_in, uint32_t site_in, float p_out,
+                                       uint64_t seed_out, uint32_t site_out, void* stream) {
+  MH_CHECK(dcol != nullptr, "layernorm_bwd_colsum: null dcol");
+  return ln_bwd_impl(dy, x, gamma, mean, rstd, dx, dx_drop, dgamma, dbeta, dcol, rows, cols, p_in, seed_in, site_in, p_out,
+                     seed_out, site_out, stream);
 }
 
 extern "C" int mh_colsum(const void* x, long long ld, float* out, int rows, int cols, void* stream) {

@@ -106,10 +106,11 @@ def attn_fwd(qkv, kv_len, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site
 
 
 def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_drop=0.0, seed=0, site=0, dq_acc=None,
-             delta=None):
+             delta=None, bias_grad=None):
     """``dq_acc``: optional fp32 [B*T, E] workspace that the caller has ALREADY zeroed (ops zeroes it on a side stream
     under the FFN backward); without it the call zeroes a fresh one itself.  ``delta``: optional precomputed
-    rowsum(dO * O) [B, heads, T] (the out_proj dgrad GEMM's EPI_DELTA epilogue); without it a kernel computes it."""
+    rowsum(dO * O) [B, heads, T] (the out_proj dgrad GEMM's EPI_DELTA epilogue); without it a kernel computes it.
+    ``bias_grad``: optional fp32 [3E] that receives (+=) the column sums of the returned dqkv."""
     E = 64 * heads
     if dout.dtype != bf16 or not dout.is_contiguous() or tuple(dout.shape) != (B * T, E):
         raise ValueError("attn_bwd: dout must be contiguous bf16 [B*T, E]")
@@ -127,8 +128,16 @@ def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_
         if dq_acc.dtype != torch.float32 or dq_acc.numel() != B * T * E or not dq_acc.is_contiguous():
             raise ValueError("attn_bwd: dq_acc must be a contiguous fp32 workspace of B*T*E elements")
         flags |= 1
+    if bias_grad is not None:
+        # ``bias_grad``: fp32 [3E], the stacked q / k / v bias gradients: the bf16 conversion of dQ and the column sums
+        # of dqkv are one pass (mh_dq_finish_colsum) instead of dq_finish + a separate column-sum kernel
+        if bias_grad.dtype != torch.float32 or bias_grad.numel() != 3 * E or not bias_grad.is_contiguous():
+            raise ValueError("attn_bwd: bias_grad must be contiguous fp32 [3E]")
+        flags |= 4
     _call("mh_attn_bwd_ex", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
           c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), c_int(flags), _s())
+    if bias_grad is not None:
+        _call("mh_dq_finish_colsum", _p(dq_acc), _p(dqkv), _p(bias_grad), c_int(B * T), c_int(E), _s())
     return dqkv
 
 
@@ -144,14 +153,22 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, *, p_drop=0.0, seed=0, site=0):
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, want_drop=False, p_in=0.0, seed_in=0, site_in=0,
-                  p_out=0.0, seed_out=0, site_out=0):
-    """Returns (dx, dx_drop or None).  dgamma / dbeta (fp32 [cols]) are accumulated in place."""
+                  p_out=0.0, seed_out=0, site_out=0, colsum_out=None):
+    """Returns (dx, dx_drop or None).  dgamma / dbeta (fp32 [cols]) are accumulated in place; so is ``colsum_out``
+    (optional fp32 [cols]): the column sums of dx_drop (of dx when there is no dx_drop)."""
     rows, cols = x.shape
     dx = torch.empty_like(x)
     dx_drop = torch.empty_like(x) if want_drop else None
-    _call("mh_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dx_drop), _p(dgamma), _p(dbeta),
-          c_int(rows), c_int(cols), _f(p_in), c_uint64(seed_in), c_uint32(site_in), _f(p_out), c_uint64(seed_out),
-          c_uint32(site_out), _s())
+    if colsum_out is None:
+        _call("mh_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dx_drop), _p(dgamma), _p(dbeta),
+              c_int(rows), c_int(cols), _f(p_in), c_uint64(seed_in), c_uint32(site_in), _f(p_out), c_uint64(seed_out),
+              c_uint32(site_out), _s())
+    else:
+        if colsum_out.dtype != torch.float32 or colsum_out.numel() != cols or not colsum_out.is_contiguous():
+            raise ValueError("layernorm_bwd: colsum_out must be contiguous fp32 [cols]")
+        _call("mh_layernorm_bwd_colsum", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dx_drop), _p(dgamma),
+              _p(dbeta), _p(colsum_out), c_int(rows), c_int(cols), _f(p_in), c_uint64(seed_in), c_uint32(site_in), _f(p_out),
+              c_uint64(seed_out), c_uint32(site_out), _s())
     return dx, dx_drop
 
 

@@ -144,8 +144,17 @@ def _flat_masked(p):
     return f is not None and f[0].flat_mask is not None
 
 
-def _wgrad(dy, x, lin, col0=0, ncols=None):
-    """lin.weight.grad += dy[:, col0:col0+n]^T @ x  (masked);  lin.bias.grad += column sums."""
+def _bias_grad_target(lin):
+    """``lin.bias.grad`` when its column sums may be accumulated by another kernel (the LayerNorm backward that produces
+    the linear layer's output gradient): trainable, and no prune mask to apply here."""
+    b, bm = param_and_mask(lin, "bias")
+    if b is None or not b.requires_grad or (bm is not None and not _flat_masked(b)):
+        return None
+    return _grad_of(b)
+
+
+def _wgrad(dy, x, lin, col0=0, ncols=None, bias_done=False):
+    """lin.weight.grad += dy[:, col0:col0+n]^T @ x  (masked);  lin.bias.grad += column sums (unless ``bias_done``)."""
     w, wm = param_and_mask(lin, "weight")
     b, bm = param_and_mask(lin, "bias")
     n = w.shape[0] if ncols is None else ncols
@@ -154,7 +163,7 @@ def _wgrad(dy, x, lin, col0=0, ncols=None):
         wm = bm = None  # the masked optimizer kernels drop the gradients of pruned elements (mh_adam_step_masked)
     if w.requires_grad:
         K.gemm(dyv, x, _grad_of(w), a_mn=True, b_mn=True, epilogue=K.EPI_F32, mask=wm)
-    if b is not None and b.requires_grad:
+    if b is not None and b.requires_grad and not bias_done:
         g = _grad_of(b)
         if bm is None:
             K.colsum_add(dyv, g)
@@ -164,7 +173,21 @@ def _wgrad(dy, x, lin, col0=0, ncols=None):
             g.add_(tmp * bm)
 
 
-def _wgrad_qkv(dqkv, x, mha, E):
+def _qkv_bias_grad_target(mha, E):
+    """The stacked [3E] q / k / v bias gradient when the three sit back to back in the flat buffer and need no mask
+    here: the attention backward's finishing pass accumulates it (``K.attn_bwd(bias_grad=...)``)."""
+    gb = []
+    for lin in (mha.q_proj, mha.k_proj, mha.v_proj):
+        b, bm = param_and_mask(lin, "bias")
+        if b is None or not b.requires_grad or b.grad is None or (bm is not None and not _flat_masked(b)) or b.numel() != E:
+            return None
+        gb.append(b.grad)
+    if gb[1].data_ptr() != gb[0].data_ptr() + 4 * E or gb[2].data_ptr() != gb[1].data_ptr() + 4 * E:
+        return None
+    return torch.as_strided(gb[0], (3 * E,), (1,))
+
+
+def _wgrad_qkv(dqkv, x, mha, E, bias_done=False):
     """Weight / bias gradients of the q, k, v projections.  When their gradients sit back to back in the flat
     buffer (trainer.trainable_params) and carry no prune masks: ONE [3E, C] wgrad GEMM and one column sum."""
     lins = (mha.q_proj, mha.k_proj, mha.v_proj)
@@ -181,10 +204,12 @@ def _wgrad_qkv(dqkv, x, mha, E):
                  and g[2].data_ptr() == g[1].data_ptr() + 4 * n and g[0].shape == g[1].shape == g[2].shape)
     if not fused:
         for i, lin in enumerate(lins):
-            _wgrad(dqkv, x, lin, col0=i * E, ncols=E)
+            _wgrad(dqkv, x, lin, col0=i * E, ncols=E, bias_done=bias_done)
         return
     C = g[0].shape[1]
     K.gemm(dqkv, x, torch.as_strided(g[0], (3 * E, C), (C, 1)), a_mn=True, b_mn=True, epilogue=K.EPI_F32)
+    if bias_done:
+        return
     gb = [b.grad if (b is not None and b.requires_grad and m is None) else None for b, m in pb]
     if all(t is not None for t in gb) and gb[1].data_ptr() == gb[0].data_ptr() + 4 * E \
             and gb[2].data_ptr() == gb[1].data_ptr() + 4 * E:
@@ -396,11 +421,12 @@ class EncoderLayerFn(torch.autograd.Function):
             dy2 = dout
             dz2 = K.dropout_apply(dout, p_res, seed, s3) if p_res > 0.0 else dout
         else:
+            b2g = _bias_grad_target(layer.fc2)  # fc2's bias gradient = column sums of dz2: accumulated by the LN backward
             dy2, dz2 = K.layernorm_bwd(dout, y2, ln2.weight.detach(), mean2, rstd2, _grad_of(ln2.weight), _grad_of(ln2.bias),
-                                       want_drop=p_res > 0.0, p_out=p_res, seed_out=seed, site_out=s3)
+                                       want_drop=p_res > 0.0, p_out=p_res, seed_out=seed, site_out=s3, colsum_out=b2g)
             if dz2 is None:
                 dz2 = dy2
-        _wgrad(dz2, u, layer.fc2)
+        _wgrad(dz2, u, layer.fc2, bias_done=not pre_ln and b2g is not None)
         dpre = torch.empty_like(pre)
         K.gemm(dz2, w2, dpre, b_mn=True, epilogue=K.EPI_DGELU, aux_in=pre, p_drop=p_act, seed=seed, site=s2)
         _wgrad(dpre, f_in, layer.fc1)
@@ -414,20 +440,22 @@ class EncoderLayerFn(torch.autograd.Function):
         else:
             dx1 = torch.empty_like(f_in)
             K.gemm(dpre, w1, dx1, b_mn=True, epilogue=K.EPI_ADD, aux_in=dy2)
+            bog = _bias_grad_target(mha.out_proj)
             dy1, dz1 = K.layernorm_bwd(dx1, y1, ln1.weight.detach(), mean1, rstd1, _grad_of(ln1.weight), _grad_of(ln1.bias),
-                                       want_drop=p_res > 0.0, p_out=p_res, seed_out=seed, site_out=s1)
+                                       want_drop=p_res > 0.0, p_out=p_res, seed_out=seed, site_out=s1, colsum_out=bog)
             if dz1 is None:
                 dz1 = dy1
         # ---- attention block ----
-        _wgrad(dz1, ctxv, mha.out_proj)
+        _wgrad(dz1, ctxv, mha.out_proj, bias_done=not pre_ln and bog is not None)
         dctx = torch.empty_like(ctxv)
         # out_proj dgrad; its epilogue also emits delta = rowsum(dO * O) per head (64-column epilogue groups = heads)
         delta = torch.empty(B, heads, T, device=dctx.device, dtype=torch.float32)
         K.gemm(dz1, wo, dctx, b_mn=True, epilogue=K.EPI_DELTA, aux_in=ctxv, delta=delta, delta_T=T)
         torch.cuda.current_stream().wait_event(zero_done)
+        bqkv = _qkv_bias_grad_target(mha, E)
         dqkv = K.attn_bwd(qkv, kv_len, ctxv, dctx, lse, keep, B, T, heads, causal=causal, p_drop=p_att, seed=seed,
-                          site=site_base + SITE_ATTN, dq_acc=dq_acc, delta=delta)
-        _wgrad_qkv(dqkv, a_in, mha, E)
+                          site=site_base + SITE_ATTN, dq_acc=dq_acc, delta=delta, bias_grad=bqkv)
+        _wgrad_qkv(dqkv, a_in, mha, E, bias_done=bqkv is not None)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)

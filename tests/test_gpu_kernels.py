@@ -139,6 +139,12 @@ def test_gemm_delta_epilogue_feeds_the_attention_backward(B, T, H, block_n):
     g_fused = k.attn_bwd(qkv, lens_t, ctx, dctx, lse, keep, B, T, H, p_drop=0.1, seed=5, site=1, delta=delta)
     g_plain = k.attn_bwd(qkv, lens_t, ctx, dctx, lse, keep, B, T, H, p_drop=0.1, seed=5, site=1)
     assert rel(g_fused, g_plain) < 2e-3  # (fp32 reduce-add order differs from launch to launch)
+    # finishing pass fused with the q / k / v bias gradients (mh_dq_finish_colsum): same dqkv, column sums accumulated
+    bg = torch.full((3 * E,), 1.0, device=DEV)
+    g_b = k.attn_bwd(qkv, lens_t, ctx, dctx, lse, keep, B, T, H, p_drop=0.1, seed=5, site=1, delta=delta, bias_grad=bg)
+    assert rel(g_b, g_plain) < 2e-3
+    want_b = g_b.float().sum(0)
+    torch.testing.assert_close(bg - 1.0, want_b, rtol=1e-3, atol=1e-3 * float(want_b.abs().max()) + 1e-3)
     with pytest.raises(RuntimeError):
         k.gemm(dz, wo.t().contiguous(), dctx, epilogue=k.EPI_DELTA, aux_in=ctx, delta=delta, delta_T=T)  # K-major B: not built
 
@@ -367,6 +373,14 @@ def test_layernorm_output_dropout_and_masked_input_gradient():
     dxa, dxd = k.layernorm_bwd(dy, x, g, mean, rstd, dg, db, want_drop=True, p_out=p, seed_out=9, site_out=11)
     m = k.dropout_apply(torch.ones_like(x), p, 9, 11) != 0
     assert rel(dxd, dxa.float() * m / (1 - p)) < 6e-3
+    # fused bias gradient: column sums of the second output (of dx when there is none), accumulated in place
+    for want_drop in (True, False):
+        cs = torch.full((cols,), 3.0, device=DEV)
+        a1, d1 = k.layernorm_bwd(dy, x, g, mean, rstd, dg, db, want_drop=want_drop, p_out=p if want_drop else 0.0,
+                                 seed_out=9, site_out=11, colsum_out=cs)
+        src = d1 if want_drop else a1
+        torch.testing.assert_close(cs - 3.0, src.float().sum(0), rtol=2e-2, atol=2e-2 * float(src.float().sum(0).abs().max()))
+        assert torch.equal(a1, dxa)
 
 
 def test_colsum_and_casts():

@@ -486,6 +486,15 @@ struct AttnBwdParams {
 //                    [ds_ready(n)] dQ(n) = dS K;  dK += dS^T Q(n);  dP(n+1)   (runs under A(n+1) / drain dQ(n))
 // A commit on s_full(n+1) also covers dV(n) (P may be overwritten), one on dp_full(n+1) covers dQ(n) / dK(n)
 // (dS may be overwritten): no further barriers are needed for the single P / dS tiles.
+#ifndef MH_BWD_TRACE
+#define MH_BWD_TRACE 0  // debug build: clock64 stamps of CTA 0's first query-block iterations (mh_attn_bwd_trace_read)
+#endif
+#if MH_BWD_TRACE
+__device__ long long g_bwd_trace[3][48][8];  // [role: compute warp 0, compute warp 15, MMA warp][iteration][stamp]
+#define BWD_STAMP(role, iter, what) do { if (blockIdx.x == 0 && (iter) < 48) g_bwd_trace[role][iter][what] = clock64(); } while (0)
+#else
+#define BWD_STAMP(role, iter, what) do { } while (0)
+#endif
 constexpr int BWD_DQ_STAGE = 128 * 64 * 4;
 constexpr int BWD_QST = 3;  // Q / dO ring depth: S(n+2) is issued in the middle of iteration n+1
 constexpr int BWD_KVLEN_CACHE = 128;  // (512 B: keeps 1 KB of the SM's shared memory free, enough for a co-resident peer-exchange CTA, peer.cu)
@@ -657,6 +666,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           const uint32_t aq = smem_u32(sQ + st * TILE_BYTES), ado = smem_u32(sdO + st * TILE_BYTES);
           // ---- P_n is in smem: dV += P^T dO (contraction over the 128 query rows), then S_{n+1}
           mbar_wait(p_ready, it & 1);
+          BWD_STAMP(2, it, 0);
           if (n == 0 && cnt > 0) mbar_wait(acc_free, (cnt - 1) & 1);  // previous item's dK / dV read out
           tc_fence_after();
 #pragma unroll
@@ -669,8 +679,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             tc_fence_after();
             issue_s(st1);
           }
+          BWD_STAMP(2, it, 1);
           // ---- dS_n is in smem: dQ_n = dS K (contraction over the 128 keys), dK += dS^T Q, then dP_{n+1}
           mbar_wait(ds_ready, it & 1);
+          BWD_STAMP(2, it, 2);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
@@ -689,6 +701,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             issue_dp(st1);
             if (n + 2 == w.n_iter) umma_commit(v_empty);
           }
+          BWD_STAMP(2, it, 3);
           st = st1; ph = ph1;
         }
         umma_commit(fin_full);
@@ -840,9 +853,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         // Instruction diet (the kernel is issue-bound: 19 executed instructions per score before, ncu): the exponent
         // argument is one packed FFMA2 per two scores, and the dropped keys are zeroed with the 16-bit pair masks that
         // two PRMTs derive from one shifted copy of the keep word (keep_bit_pos2 layout) instead of per-bit tests.
+#if MH_BWD_TRACE
+        const int trole = (warp == 0 && lane == 0) ? 0 : ((warp == 15 && lane == 0) ? 1 : -1);
+#define CSTAMP(what) do { if (trole >= 0) BWD_STAMP(trole, it, what); } while (0)
+#else
+#define CSTAMP(what) do { } while (0)
+#endif
+        CSTAMP(0);
         if (n == 0 && cnt > 0) mbar_wait(kv_st_free, (cnt - 1) & 1);  // previous item's dK / dV left the P / dS tiles
         mbar_wait(s_full, it & 1);
         tc_fence_after();
+        CSTAMP(1);
         {
           uint32_t sa[16], sb[16];
           tmem_ld16(tm_s + lane_off + kc0, sa);
@@ -878,13 +899,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);  // one arrival per warp: 512 arrivals on one mbarrier serialise
+        CSTAMP(2);
         // ---- dQ of the previous query block (its MMA ran under phase A)
         if (n > 0) drain_dq(it - 1);
+        CSTAMP(3);
         // ---- phase B: dS = P (c u - c delta / s), bf16 -> smem
         // u = keep ? dP : 0 as a bitwise AND with 32-bit masks (one PRMT each: the sign of byte 1 / 3 / 0 / 2 of the
         // shifted keep word replicated over the word), then packed fp32: FFMA2 (c u - c delta / s), FMUL2 (x P).
         mbar_wait(dp_full, it & 1);
         tc_fence_after();
+        CSTAMP(4);
         {
           uint32_t da[8], db[8];
           tmem_ld8(tm_dp + lane_off + kc0, da);
@@ -915,6 +939,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_ready);
+        CSTAMP(5);
       }
       if (w.n_iter > 0) drain_dq(it - 1);
       // final dK / dV: row r = key k0 + r, this warp's 16 head-dim columns
@@ -1096,6 +1121,14 @@ extern "C" int mh_attn_fwd(const void* qkv, const int* kv_len, void* out, float*
   ++g_launches;
   return 0;
 }
+
+#if MH_BWD_TRACE
+extern "C" int mh_attn_bwd_trace_read(long long* host_out) {  // debug builds only: 3 x 48 x 8 clock64 stamps of CTA 0
+  MH_CUDA(cudaDeviceSynchronize());
+  MH_CUDA(cudaMemcpyFromSymbol(host_out, g_bwd_trace, sizeof(long long) * 3 * 48 * 8));
+  return 0;
+}
+#endif
 
 #if MH_F2_TRACE
 extern "C" int mh_attn_trace_read(long long* host_out) {  // debug builds only: 8 x 64 x 8 clock64 stamps

@@ -20,6 +20,10 @@
 // latter is what wgrad (dW = dY^T X) needs and avoids any transpose kernel.  MH_EPI_F32 accumulates with
 // cp.reduce.async.bulk (.add.f32), which makes split-K and gradient accumulation the same code path.
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "mh_b200.h"
 #define MH_PDL_FAMILY 1
@@ -684,10 +688,45 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// Descriptor cache ("the library owns only immutable caches: TMA descriptors keyed by ptr / shape / stride").
+// An eager training step encodes ~750 tensor maps on the host (5 per GEMM launch) for the same few hundred (pointer,
+// shape) pairs every step -- activations come back from the caching allocator at the same addresses; a CUtensorMap is a
+// pure function of its key, so entries never go stale.  Behind a mutex: backward runs on autograd's worker thread.
+struct TmapKey {
+  const void* base;
+  long long d[5];
+  int b[4];
+  bool operator==(const TmapKey& o) const { return base == o.base && !memcmp(d, o.d, sizeof(d)) && !memcmp(b, o.b, sizeof(b)); }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    for (long long v : k.d) h = (h ^ static_cast<uint64_t>(v)) * 0x100000001B3ull;
+    for (int v : k.b) h = (h ^ static_cast<uint64_t>(static_cast<uint32_t>(v))) * 0x100000001B3ull;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmap_cache.find(k);
+  if (it == g_tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+static void tmap_insert(const TmapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();  // bounded: a long run with changing shapes starts over
+  g_tmap_cache.emplace(k, m);
+}
+
 // 2-D bf16 row-major array [rows][cols] (leading dim ld elements), box = {box_cols, box_rows},
 // 128-byte swizzle, out-of-bounds reads return zeros.
 int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_cols,
                  int box_rows, int elem_bytes = 2, int swizzle_bytes = 128) {
+  const TmapKey key{base, {rows, cols, ld, 0, 2}, {box_cols, box_rows, elem_bytes, swizzle_bytes}};
+  if (tmap_lookup(key, out)) return 0;
   EncodeTiledFn enc = get_encode_tiled();
   MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -702,12 +741,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
            static_cast<int>(r), rows, cols, ld, box_cols, box_rows);
+  tmap_insert(key, *out);
   return 0;
 }
 
 // 3-D variant used by attention: [d2][d1][d0] with strides in elements.
 int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1, long long d2, long long stride1,
                  long long stride2, int box0, int box1, int elem_bytes) {
+  const TmapKey key{base, {d0, d1, d2, stride1, stride2 ^ (3LL << 60)}, {box0, box1, elem_bytes, 128}};
+  if (tmap_lookup(key, out)) return 0;
   EncodeTiledFn enc = get_encode_tiled();
   MH_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   MH_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -721,6 +763,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, long long d0, long long d1,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with %d", static_cast<int>(r));
+  tmap_insert(key, *out);
   return 0;
 }
 

@@ -920,10 +920,21 @@ extern "C" int mh_gemm(const mh_gemm_args* a, void* stream) {
   if (out_f32) {
     splits = a->split_k;
     if (splits <= 0) {
-      splits = units / (tiles_m * num_n);
-      if (splits < 1) splits = 1;
-      if (splits > kblocks / 4) splits = kblocks / 4 > 0 ? kblocks / 4 : 1;  // keep >= 4 k-blocks per split
-      if (splits > 32) splits = 32;
+      // Work units = tiles x splits, `units` of them run at a time: pick the split count that minimises
+      // waves x (k-blocks per unit + a fixed per-unit cost: pipeline fill and the part of the reduce-add epilogue the next
+      // unit's main loop does not hide, ~6 k-blocks).  "units / tiles" alone left the fused QKV weight gradient (27 tiles on
+      // 74 CTA pairs) at 2 splits = 54 units = 73 % of the chip; 8 splits = 216 units = 2.92 waves.
+      const int tiles_mn = tiles_m * num_n;
+      const int max_s = kblocks / 4 > 0 ? (kblocks / 4 < 32 ? kblocks / 4 : 32) : 1;  // keep >= 4 k-blocks per split
+      long best_cost = -1;
+      splits = 1;
+      for (int sp = 1; sp <= max_s; ++sp) {
+        const int per = (kblocks + sp - 1) / sp;
+        const int eff = (kblocks + per - 1) / per;  // no empty trailing splits
+        const long waves = (static_cast<long>(tiles_mn) * eff + units - 1) / units;
+        const long cost = waves * (per + 6);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = eff; }
+      }
     }
     if (splits > kblocks) splits = kblocks;
     // avoid empty trailing splits

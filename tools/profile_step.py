@@ -21,6 +21,7 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--frames", type=int, default=750)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--list", type=int, default=0, help="also print the last N kernel launches in stream order (name, us)")
 args = ap.parse_args()
 
 np.random.seed(1337)
@@ -44,9 +45,11 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 wall_ms = e0.elapsed_time(e1) / args.steps
 agg = collections.defaultdict(lambda: [0, 0.0])
 spans = []
+order = []
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         name = ev.name.split("(")[0][:90]
+        order.append((ev.time_range.start, name, ev.time_range.end - ev.time_range.start))
         agg[name][0] += 1
         agg[name][1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
         spans.append((ev.time_range.start, ev.time_range.end))
@@ -66,3 +69,8 @@ print(f"wall {wall_ms:.2f} ms/step   sum of kernel durations {tot / 1e3 / args.s
       f"GPU busy (union) {busy / 1e3 / args.steps:.2f} ms/step")
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:45]:
     print(f"{t / args.steps:10.1f} us/step {100 * t / tot:5.1f}%  n/step={n / args.steps:6.1f} avg={t / n:8.1f} us  {k}")
+if args.list:
+    order.sort()
+    print(f"--- last {args.list} launches in stream order")
+    for _, name, us in order[-args.list:]:
+        print(f"{us:9.1f} us  {name}")

@@ -35,8 +35,11 @@ constexpr int ln_fwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * nch * 
 // (profiles/r01_q_ncu_ln_fwd.txt): the output stays in L2, DRAM sees 2 TB/s, issue slots are 33 % busy and 46 % of
 // the stalls are long-scoreboard -- the kernel is bound by the latency chain of one row per warp (load -> two
 // dependent shuffle reductions -> store), not by bandwidth; interleaving two rows per warp is the open lever.
-template <int NCH, bool EXACT>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+#ifndef LN_FWD_MINB
+#define LN_FWD_MINB 3
+#endif
+template <int NCH, bool EXACT, bool HAS_DROP>
+__global__ void __launch_bounds__(LN_WARPS * 32, LN_FWD_MINB)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
               int cols_rt, float eps, const DropCfg drop) {
@@ -62,57 +65,88 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   };
   issue(warp_global, 0);
   issue(warp_global + nwarps, 1);
+  // gamma / beta of this lane's columns live in registers for the whole kernel (48 registers at 768 columns): reloading
+  // them for every row put 6 KB per row through L1 next to 4.5 KB of row traffic (ring fill, ring read, store) and made the
+  // L1 / shared-memory data path, not HBM, the limit (20.7 us against 8.8 us for a copy of the same tensor)
+  uint64_t g[NCH][4], bt[NCH][4];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    if (EXACT || lane + 32 * i < nchunks) {
+      const int c8 = lane * 8 + i * 256;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 + 4));
+      g[i][0] = pack2f(g0.x, g0.y); g[i][1] = pack2f(g0.z, g0.w); g[i][2] = pack2f(g1.x, g1.y); g[i][3] = pack2f(g1.z, g1.w);
+      bt[i][0] = pack2f(b0.x, b0.y); bt[i][1] = pack2f(b0.z, b0.w); bt[i][2] = pack2f(b1.x, b1.y); bt[i][3] = pack2f(b1.z, b1.w);
+    }
+  }
   int stage = 0;
   for (int row = warp_global; row < rows; row += nwarps) {
     issue(row + 2 * nwarps, stage + 2 >= LNB_STAGES ? stage + 2 - LNB_STAGES : stage + 2);
     // keep bits of this lane's chunks (bit-sliced dropout: 32 decisions per generated word), produced while the row is
     // still in flight -- the kernel is latency-bound, the Philox rounds are free here
     uint32_t kb[NCH];
-    if (drop.thresh != 0) dstate.keep_bytes_row<NCH>(drop, static_cast<uint64_t>(row) * (nchunks >> 2), nchunks, lane, kb);
+    if (HAS_DROP) dstate.keep_bytes_row<NCH>(drop, static_cast<uint64_t>(row) * (nchunks >> 2), nchunks, lane, kb);
     cp_async_wait<2>();
-    float v[NCH][8];
-    float s = 0.f;
+    // packed fp32 pairs (FADD2 / FFMA2): the kernel is issue- and latency-bound (a plain copy of the same L2-resident
+    // tensor takes 8.8 us), not HBM-bound -- 10.9 executed instructions per element before, ~7 now
+    // the row stays in registers as raw bf16 (12 registers at 768 columns) and is unpacked once per pass: with gamma / beta
+    // resident, fp32 copies of the row would push the kernel below three blocks per SM
+    uint4 raw[NCH];
+    auto unpack = [](const uint4& q, uint64_t (&o)[4]) {
+      o[0] = pack2f(bf16_lo(q.x), bf16_hi(q.x));
+      o[1] = pack2f(bf16_lo(q.y), bf16_hi(q.y));
+      o[2] = pack2f(bf16_lo(q.z), bf16_hi(q.z));
+      o[3] = pack2f(bf16_lo(q.w), bf16_hi(q.w));
+    };
+    uint64_t sa = pack2f(0.f, 0.f), sb = sa;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       if (EXACT || lane + 32 * i < nchunks) {
-        bf16x8_to_f32(lds128(ring + (stage * NCH + i) * 512), v[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[i][j];
+        raw[i] = lds128(ring + (stage * NCH + i) * 512);
+        uint64_t v[4];
+        unpack(raw[i], v);
+        sa = fadd2(sa, fadd2(v[0], v[1]));  // two accumulators: half the dependent chain
+        sb = fadd2(sb, fadd2(v[2], v[3]));
       }
     }
-    const float mean = warp_sum(s) * inv_cols;
-    float sq = 0.f;
+    float s0, s1;
+    unpack2f(fadd2(sa, sb), s0, s1);
+    const float mean = warp_sum(s0 + s1) * inv_cols;
+    const uint64_t nmean2 = pack2f(-mean, -mean);
+    uint64_t qa = pack2f(0.f, 0.f), qb = qa;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       if (EXACT || lane + 32 * i < nchunks) {
+        uint64_t v[4];
+        unpack(raw[i], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
-          sq = fmaf(d, d, sq);
+        for (int k = 0; k < 4; k += 2) {
+          const uint64_t d0 = fadd2(v[k], nmean2), d1 = fadd2(v[k + 1], nmean2);
+          qa = ffma2(d0, d0, qa);
+          qb = ffma2(d1, d1, qb);
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_cols + eps);
+    unpack2f(fadd2(qa, qb), s0, s1);
+    const float rstd = rsqrtf(warp_sum(s0 + s1) * inv_cols + eps);
     if (lane == 0) {
       mean_out[row] = mean;
       rstd_out[row] = rstd;
     }
     __nv_bfloat16* yr = y + static_cast<long long>(row) * cols + lane * 8;
     const float nmr = -mean * rstd;
+    const uint64_t rstd2 = pack2f(rstd, rstd), nmr2 = pack2f(nmr, nmr);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       if (EXACT || lane + 32 * i < nchunks) {
-        const int c8 = lane * 8 + i * 256;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 + 4));
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint64_t v[4];
+        unpack(raw[i], v);
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[i][j], rstd, nmr), g[j], b[j]);
-        if (drop.thresh != 0) DropState::apply8(drop, kb[i], o);
+        for (int k = 0; k < 4; ++k) unpack2f(ffma2(ffma2(v[k], rstd2, nmr2), g[i][k], bt[i][k]), o[2 * k], o[2 * k + 1]);
+        if (HAS_DROP) DropState::apply8(drop, kb[i], o);
         stg128(yr + i * 256, f32_to_bf16x8(o));
       }
     }
@@ -378,9 +412,9 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restri
   }
 }
 
-template <int NCH, bool EXACT, typename... Args>
+template <int NCH, bool EXACT, bool HAS_DROP, typename... Args>
 static int launch_ln_fwd(int grid, cudaStream_t st, Args... args) {
-  auto kfn = ln_fwd_kernel<NCH, EXACT>;
+  auto kfn = ln_fwd_kernel<NCH, EXACT, HAS_DROP>;
   static bool configured = false;
   if (!configured) {
     MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_fwd_smem_bytes(NCH)));
@@ -499,14 +533,16 @@ extern "C" int mh_layernorm_fwd(const void* x, const float* gamma, const float* 
              reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
            "layernorm: x, y, gamma and beta must be 16-byte aligned (rows are moved as 16-byte chunks)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // resident blocks only (4 per SM at 64 registers / 37 KB of ring): a warp then walks >= 5 rows at the bench shape
+  // resident blocks only (LN_FWD_MINB per SM: gamma / beta stay in registers): a warp then walks ~10 rows at the bench shape
   // and its ring stays primed
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * 4);
+  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_FWD_MINB);
   const DropCfg d = make_drop(p_drop, seed, site);
   return dispatch_nch(cols, [&](auto nch, auto exact) {
-    const int rc = launch_ln_fwd<decltype(nch)::value, decltype(exact)::value>(
-        grid, st, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, rows, cols,
-        eps, d);
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    const int rc = d.thresh != 0
+        ? launch_ln_fwd<decltype(nch)::value, decltype(exact)::value, true>(grid, st, xp, gamma, beta, yp, mean, rstd, rows, cols, eps, d)
+        : launch_ln_fwd<decltype(nch)::value, decltype(exact)::value, false>(grid, st, xp, gamma, beta, yp, mean, rstd, rows, cols, eps, d);
     if (rc != 0) return rc;
     ++g_launches;
     return 0;

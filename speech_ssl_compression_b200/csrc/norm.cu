@@ -158,143 +158,140 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 // Backward.  dy_eff = dy (* keep mask of the output dropout `din`, if the forward dropped the
 // LN output).  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).
 // Also emits dx_drop = dx * keep mask of `dout` (the dropout that sat on the GEMM output
-// feeding this LayerNorm's input) so the dgrad/wgrad GEMMs can consume it directly.
+// feeding this LayerNorm's input) so the dgrad/wgrad GEMMs can consume it directly, and (HAS_DCOL) the column sums of
+// that second output -- the bias gradient of the GEMM that fed this LayerNorm's input (out_proj / fc2), which otherwise
+// costs a separate pass over the same tensor.
 //
-// The first version ran 42 instructions per element with the row and its prefetched successor in registers: it
-// was issue-bound (3.1 TB/s) and one step from spilling.  Now:
-//  * rows are staged through shared memory by 16-byte cp.async (LDGSTS, L2 -> smem, no registers): every warp owns a
-//    3-deep ring of (dy, x) rows, two rows are always in flight while one is reduced, and both passes read the row
-//    from its slot (lane-private 16-byte slots: no bank conflicts, no cross-lane synchronisation -- a lane only
-//    reads what it copied itself, cp.async.wait_group orders that);
-//  * pass 1 is xhat = fma(x, rstd, -mean rstd) plus four fused accumulations; pass 2 is
-//      dx = dy (rstd g) + x (-rstd^2 s2) + (-rstd (s1 - mean rstd s2))   -- one FMUL and two FMAs per element;
-//  * dropout round keys are constant-bank operands (DropState), EXACT drops the chunk predicates, the rare
-//    input-dropout path (one LayerNorm per step) is a template parameter.
+// History: (1) one warp per row, row and prefetched successor in registers: 42 instructions per element, issue-bound,
+// 3.1 TB/s.  (2) rows through a per-warp cp.async ring, packed fp32: 36 us for the step's form, 16 warps per SM at 124
+// registers (72 of them the per-lane dgamma / dbeta / dcol accumulators of 24 columns) and, per ncu, the L1 / shared-memory
+// data path as the busiest unit (67 %): 18 KB per row went through it (ring fill 3, two passes of ring reads 6, gamma
+// twice 6, stores 3).  (3) now: NCH warps per row, one 8-column chunk per lane.  gamma (8 registers), the raw bf16 row
+// (8) and the accumulators (24) all stay in registers, so a row costs 9 KB of L1 traffic (ring fill, one ring read,
+// stores) and the kernel runs 24+ warps per SM; the row statistics cross the NCH warps through 8 bytes of shared memory
+// and one named barrier per row; the dropout words of four consecutive rows of a warp come from ONE Philox pass (lane
+// l generates word l & 7 of row l >> 3).
 #ifndef LN_BWD_MINB
 #define LN_BWD_MINB 2
 #endif
-#ifndef LN_BWD_GRID_MULT
-#define LN_BWD_GRID_MULT 2
-#endif
-constexpr int ln_bwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * 2 * nch * 512; }
+constexpr int LNB_RPB = 4;  // row slots per block: a block is LNB_RPB x NCH warps
+constexpr int ln_bwd_smem_bytes(int nch) { return LNB_RPB * nch * LNB_STAGES * 2 * 512; }
 
-// HAS_DCOL: also accumulate the column sums of the (dropout-applied) output into dcol -- the bias gradient of the GEMM
-// that fed this LayerNorm's input (out_proj / fc2), which otherwise costs a separate pass over the same tensor
 template <int NCH, bool EXACT, bool HAS_DIN, bool HAS_DCOL>
-__global__ void __launch_bounds__(LN_WARPS * 32, LN_BWD_MINB)
+__global__ void __launch_bounds__(LNB_RPB * NCH * 32, LN_BWD_MINB)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dcol, int rows, int cols_rt, const DropCfg din, const DropCfg dout) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t lnb_ring[];
-  __shared__ __align__(16) float red[LN_WARPS][32 * 8 + 4];
+  __shared__ float2 part_stats[LNB_RPB][2][NCH];            // (s1, s2) partial sums of a row, double-buffered by row parity
+  __shared__ __align__(16) float red[LNB_RPB][NCH * 256 + 4];  // final cross-slot reduction of the column accumulators
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int warp_global = blockIdx.x * LN_WARPS + warp;
-  const int nwarps = gridDim.x * LN_WARPS;
+  const int slot = warp / NCH, part = warp - slot * NCH;
+  const int row_stride = gridDim.x * LNB_RPB;
   const int cols = EXACT ? NCH * 256 : cols_rt;
   const int nchunks = EXACT ? NCH * 32 : cols_rt >> 3;
+  const int chunk = part * 32 + lane;  // this lane's 8-column chunk of the row
+  const bool has_chunk = EXACT || chunk < nchunks;
   const float inv_cols = 1.0f / static_cast<float>(cols);
+  const bool drop_out = dx_drop != nullptr && dout.thresh != 0;
   const DropState st_in(din), st_out(dout);  // (st_in is dead code unless HAS_DIN)
-  // ring slot of (stage, dy|x, chunk i) for this lane: 512 bytes per (stage, tensor, chunk), 16 bytes per lane
-  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(lnb_ring)) + warp * (LNB_STAGES * 2 * NCH * 512) + lane * 16;
-  auto slot = [&](int stage, int which, int i) -> uint32_t { return ring + ((stage * 2 + which) * NCH + i) * 512; };
+  // ring slot of (stage, dy | x) for this lane: 512 bytes per (stage, tensor), 16 bytes per lane
+  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(lnb_ring)) + warp * (LNB_STAGES * 2 * 512) + lane * 16;
+  auto slot_addr = [&](int stage, int which) -> uint32_t { return ring + (stage * 2 + which) * 512; };
   auto issue = [&](int row, int stage) {
-    if (row < rows) {
-      const long long off = static_cast<long long>(row) * cols + lane * 8;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        if (EXACT || lane + 32 * i < nchunks) {
-          cp_async16(slot(stage, 0, i), dy + off + i * 256);
-          cp_async16(slot(stage, 1, i), x + off + i * 256);
-        }
-      }
+    if (row < rows && has_chunk) {
+      const long long off = static_cast<long long>(row) * cols + chunk * 8;
+      cp_async16(slot_addr(stage, 0), dy + off);
+      cp_async16(slot_addr(stage, 1), x + off);
     }
     cp_async_commit();  // (an empty group past the end keeps the wait_group count uniform)
   };
-  // Column accumulators and all per-element arithmetic are packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two lanes per issued
-  // instruction).  ncu on the scalar version: 19.5 executed instructions per element, issue slots 45 % busy with 16 warps per
-  // SM -- as much issue- as HBM-bound.
-  uint64_t dg[NCH][4], db[NCH][4], dc[HAS_DCOL ? NCH : 1][4];
-  const uint64_t zero2 = pack2f(0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < NCH; ++i)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dg[i][k] = db[i][k] = zero2;
-#pragma unroll
-  for (int i = 0; i < (HAS_DCOL ? NCH : 1); ++i)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dc[i][k] = zero2;
-  // one row chunk (8 bf16) -> four fp32 pairs; gamma chunk -> four pairs
   auto unpack8 = [](uint4 q, uint64_t (&o)[4]) {
     o[0] = pack2f(bf16_lo(q.x), bf16_hi(q.x));
     o[1] = pack2f(bf16_lo(q.y), bf16_hi(q.y));
     o[2] = pack2f(bf16_lo(q.z), bf16_hi(q.z));
     o[3] = pack2f(bf16_lo(q.w), bf16_hi(q.w));
   };
-  auto load_gamma = [&](int i, uint64_t (&g)[4]) {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + i * 256 + 4));
-    g[0] = pack2f(g0.x, g0.y); g[1] = pack2f(g0.z, g0.w); g[2] = pack2f(g1.x, g1.y); g[3] = pack2f(g1.z, g1.w);
+  // the keep words of FOUR consecutive rows of this warp come from one Philox pass: lane l generates word (l & 7) of this
+  // warp's 8 words (32 chunks x 8 bits) of row `row + (l >> 3) * row_stride`; every row then fetches its byte by shuffle
+  auto gen_keep4 = [&](const DropState& st, const DropCfg& d, int row) -> uint32_t {
+    const int r = row + (lane >> 3) * row_stride;
+    const int w = part * 8 + (lane & 7);
+    return (r < rows && w < (nchunks >> 2)) ? st.keep32(d, static_cast<uint64_t>(r) * (nchunks >> 2) + w) : 0xffffffffu;
   };
-  // upstream gradient chunk, with the (rare: one LayerNorm per step) dropout of the forward's LN output applied
-  auto load_dy = [&](int stage, int i, uint32_t kin_i, uint64_t (&d)[4]) {
-    const uint4 q = lds128(slot(stage, 0, i));
-    if (HAS_DIN) {
-      float f[8];
-      bf16x8_to_f32(q, f);
-      DropState::apply8(din, kin_i, f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] = pack2f(f[2 * k], f[2 * k + 1]);
-    } else {
-      unpack8(q, d);
-    }
+  auto keep_byte = [&](uint32_t cache, int sub) -> uint32_t {
+    return (__shfl_sync(0xffffffffu, cache, sub * 8 + (lane >> 2)) >> (8 * (lane & 3))) & 0xffu;
   };
 
-  issue(warp_global, 0);
-  issue(warp_global + nwarps, 1);
-  float nmean = 0.f, nrstd = 0.f;
-  if (warp_global < rows) {
-    nmean = __ldg(mean_in + warp_global);
-    nrstd = __ldg(rstd_in + warp_global);
+  const uint64_t zero2 = pack2f(0.f, 0.f);
+  uint64_t dg[4], db[4], dc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dg[k] = db[k] = dc[k] = zero2;
+  uint64_t g[4] = {zero2, zero2, zero2, zero2};
+  if (has_chunk) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + chunk * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + chunk * 8 + 4));
+    g[0] = pack2f(g0.x, g0.y); g[1] = pack2f(g0.z, g0.w); g[2] = pack2f(g1.x, g1.y); g[3] = pack2f(g1.z, g1.w);
   }
-  int stage = 0;
-  for (int row = warp_global; row < rows; row += nwarps) {
-    {  // refill the slot that was consumed in the previous trip (this thread's reads of it have retired)
+
+  const int row0 = blockIdx.x * LNB_RPB + slot;
+  issue(row0, 0);
+  issue(row0 + row_stride, 1);
+  float nmean = 0.f, nrstd = 0.f;
+  if (row0 < rows) {
+    nmean = __ldg(mean_in + row0);
+    nrstd = __ldg(rstd_in + row0);
+  }
+  int stage = 0, it = 0;
+  uint32_t kin_cache = 0xffffffffu, kout_cache = 0xffffffffu;
+  // every warp of a row slot walks the same rows: the named barrier below is uniform within the slot
+  for (int row = row0; row < rows; row += row_stride, ++it) {
+    {  // refill the ring slot that was consumed in the previous trip (this thread's reads of it have retired)
       const int s2 = stage + 2 >= LNB_STAGES ? stage + 2 - LNB_STAGES : stage + 2;
-      issue(row + 2 * nwarps, s2);
+      issue(row + 2 * row_stride, s2);
     }
     const float rstd = nrstd, nmr = -nmean * nrstd;
-    uint32_t kin[NCH], kout[NCH];  // keep bits of this lane's chunks under the two dropouts (generated under the loads)
-    if (row + nwarps < rows) {
-      nmean = __ldg(mean_in + row + nwarps);
-      nrstd = __ldg(rstd_in + row + nwarps);
+    if (row + row_stride < rows) {
+      nmean = __ldg(mean_in + row + row_stride);
+      nrstd = __ldg(rstd_in + row + row_stride);
     }
-    const uint64_t word0 = static_cast<uint64_t>(row) * (nchunks >> 2);  // dropout stream word of the row's first element
-    if (HAS_DIN) st_in.keep_bytes_row<NCH>(din, word0, nchunks, lane, kin);
-    if (dx_drop != nullptr && dout.thresh != 0) st_out.keep_bytes_row<NCH>(dout, word0, nchunks, lane, kout);
+    if ((it & 3) == 0) {  // (generated under the loads)
+      if (HAS_DIN) kin_cache = gen_keep4(st_in, din, row);
+      if (drop_out) kout_cache = gen_keep4(st_out, dout, row);
+    }
     cp_async_wait<2>();  // everything but the two youngest groups has landed: this row is in its slot
-    const long long off = static_cast<long long>(row) * cols + lane * 8;
-    const uint64_t rstd2 = pack2f(rstd, rstd), nmr2 = pack2f(nmr, nmr);
-    uint64_t s1p = zero2, s2p = zero2;
+    uint64_t d[4] = {zero2, zero2, zero2, zero2}, xv[4] = {zero2, zero2, zero2, zero2};
+    uint32_t kin_b = 0xffu, kout_b = 0xffu;  // (the shuffles need all 32 lanes: outside the per-chunk predicate)
+    if (HAS_DIN) kin_b = keep_byte(kin_cache, it & 3);
+    if (drop_out) kout_b = keep_byte(kout_cache, it & 3);
+    if (has_chunk) {
+      const uint4 qd = lds128(slot_addr(stage, 0));
+      if (HAS_DIN) {
+        float f[8];
+        bf16x8_to_f32(qd, f);
+        DropState::apply8(din, kin_b, f);
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      if (EXACT || lane + 32 * i < nchunks) {
-        uint64_t d[4], xv[4], g[4];
-        load_dy(stage, i, HAS_DIN ? kin[i] : 0u, d);
-        unpack8(lds128(slot(stage, 1, i)), xv);
-        load_gamma(i, g);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t t = fmul2(d[k], ffma2(xv[k], rstd2, nmr2));  // dy * xhat
-          s1p = ffma2(d[k], g[k], s1p);
-          s2p = ffma2(t, g[k], s2p);
-          dg[i][k] = fadd2(dg[i][k], t);
-          db[i][k] = fadd2(db[i][k], d[k]);
-        }
+        for (int k = 0; k < 4; ++k) d[k] = pack2f(f[2 * k], f[2 * k + 1]);
+      } else {
+        unpack8(qd, d);
       }
+      unpack8(lds128(slot_addr(stage, 1)), xv);
     }
+    // pass 1: xhat, the two row sums, the column accumulators
+    uint64_t s1p = zero2, s2p = zero2, xh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xh[k] = ffma2(xv[k], pack2f(rstd, rstd), pack2f(nmr, nmr));
+      const uint64_t t = fmul2(d[k], xh[k]);  // dy * xhat
+      s1p = ffma2(d[k], g[k], s1p);
+      s2p = ffma2(t, g[k], s2p);
+      dg[k] = fadd2(dg[k], t);
+      db[k] = fadd2(db[k], d[k]);
+    }
+    // (lanes past the last chunk hold dy = 0: they add nothing to the sums and store nothing)
     float s1, s2;
     {
       float a0, a1, b0, b1;
@@ -307,61 +304,57 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
+      if (NCH > 1) {  // across the row's NCH warps: 8 bytes each through shared memory, one named barrier
+        if (lane == 0) part_stats[slot][it & 1][part] = make_float2(s1, s2);
+        bar_sync(1 + slot, NCH * 32);
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NCH; ++w) {
+          const float2 ps = part_stats[slot][it & 1][w];
+          s1 += ps.x;
+          s2 += ps.y;
+        }
+      }
       s1 *= inv_cols;
       s2 *= inv_cols;
     }
-    // dx = rstd (d g - s1 - xh s2),  xh = x rstd + nmr
-    const float cb = -rstd * rstd * s2;
-    const float cc = -rstd * fmaf(nmr, s2, s1);
-    const uint64_t cb2 = pack2f(cb, cb), cc2 = pack2f(cc, cc);
+    // pass 2: dx = rstd (d g - s1 - xh s2)
+    const float c0 = -rstd * s1, c1 = -rstd * s2;
+    const uint64_t c02 = pack2f(c0, c0), c12 = pack2f(c1, c1), rstd2 = pack2f(rstd, rstd);
+    float o[8];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      if (EXACT || lane + 32 * i < nchunks) {
-        uint64_t d[4], xv[4], g[4];
-        load_dy(stage, i, HAS_DIN ? kin[i] : 0u, d);
-        unpack8(lds128(slot(stage, 1, i)), xv);
-        load_gamma(i, g);
-        float o[8];
+    for (int k = 0; k < 4; ++k) unpack2f(ffma2(d[k], fmul2(g[k], rstd2), ffma2(xh[k], c12, c02)), o[2 * k], o[2 * k + 1]);
+    if (has_chunk) {
+      const long long off = static_cast<long long>(row) * cols + chunk * 8;
+      stg128(dx + off, f32_to_bf16x8(o));
+      if (dx_drop != nullptr) {
+        if (drop_out) DropState::apply8(dout, kout_b, o);
+        stg128(dx_drop + off, f32_to_bf16x8(o));
+      }
+      if (HAS_DCOL) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          unpack2f(ffma2(d[k], fmul2(g[k], rstd2), ffma2(xv[k], cb2, cc2)), o[2 * k], o[2 * k + 1]);
-        stg128(dx + off + i * 256, f32_to_bf16x8(o));
-        if (dx_drop != nullptr) {
-          if (dout.thresh != 0) DropState::apply8(dout, kout[i], o);
-          stg128(dx_drop + off + i * 256, f32_to_bf16x8(o));
-        }
-        if (HAS_DCOL) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dc[i][k] = fadd2(dc[i][k], pack2f(o[2 * k], o[2 * k + 1]));
-        }
+        for (int k = 0; k < 4; ++k) dc[k] = fadd2(dc[k], pack2f(o[2 * k], o[2 * k + 1]));
       }
     }
     stage = stage + 1 == LNB_STAGES ? 0 : stage + 1;
   }
   cp_async_wait<0>();
-  // block reduction of the per-warp partial dgamma / dbeta, then one atomic per column
+  // block reduction of the per-warp partial dgamma / dbeta (/ dcol) over the row slots, then one atomic per column
   for (int pass = 0; pass < (HAS_DCOL ? 3 : 2); ++pass) {
+    __syncthreads();
+    {
+      float f[8];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      __syncthreads();
-      {
-        float f[8];
+      for (int k = 0; k < 4; ++k) unpack2f(pass == 0 ? dg[k] : (pass == 1 ? db[k] : dc[k]), f[2 * k], f[2 * k + 1]);
+      *reinterpret_cast<float4*>(&red[slot][chunk * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(&red[slot][chunk * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += LNB_RPB * NCH * 32) {
+      float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          unpack2f(pass == 0 ? dg[i][k] : (pass == 1 ? db[i][k] : dc[HAS_DCOL ? i : 0][k]), f[2 * k], f[2 * k + 1]);
-        // two 16-byte stores per lane (the scalar stores at a stride of 8 floats were 8-way bank conflicts)
-        *reinterpret_cast<float4*>(&red[warp][lane * 8]) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(&red[warp][lane * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
-      }
-      __syncthreads();
-      const int c = threadIdx.x;  // 256 threads <-> 256 columns of this chunk group
-      const int col = (32 * i) * 8 + c;
-      if (col < cols) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) t += red[w][c];
-        atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dcol)) + col, t);
-      }
+      for (int sidx = 0; sidx < LNB_RPB; ++sidx) t += red[sidx][c];
+      atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dcol)) + c, t);
     }
   }
 }
@@ -432,7 +425,7 @@ static int launch_ln_bwd(int grid, cudaStream_t st, Args... args) {
     MH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_bwd_smem_bytes(NCH)));
     configured = true;
   }
-  MH_CUDA(launch_pdl(kfn, dim3(grid), dim3(LN_WARPS * 32), ln_bwd_smem_bytes(NCH), st, args...));
+  MH_CUDA(launch_pdl(kfn, dim3(grid), dim3(LNB_RPB * NCH * 32), ln_bwd_smem_bytes(NCH), st, args...));
   return 0;
 }
 
@@ -561,7 +554,7 @@ static int ln_bwd_impl(const void* dy, const void* x, const float* gamma, const 
              reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop)) & 15) == 0,
            "layernorm_bwd: dy, x, gamma, dx and dx_drop must be 16-byte aligned (rows are moved as 16-byte chunks)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sm_count() * LN_BWD_GRID_MULT);
+  const int grid = min((rows + LNB_RPB - 1) / LNB_RPB, sm_count() * LN_BWD_MINB);
   const DropCfg din = make_drop(p_in, seed_in, site_in), dout = make_drop(p_out, seed_out, site_out);
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);

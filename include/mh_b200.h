@@ -105,6 +105,13 @@ int mh_dq_finish_colsum(const float* dq_acc, void* dqkv, float* colsum, int rows
 int mh_attn_bwd_ex(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                    const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads, int causal,
                    float p_drop, uint64_t seed, uint32_t site, int flags, void* stream);
+/* mh_attn_bwd_bias: mh_attn_bwd_ex (flags 1 and 2) that also produces the stacked q / k / v bias gradients
+ * (fairseq_code/multihead_attention.py:151: the three in_proj biases), bias_grad[0:3E] += column sums of dqkv.  The k / v
+ * parts are reduced inside the attention backward from its fp32 dK / dV accumulators (a 31-shuffle transposing butterfly per
+ * warp and key block), the q part in the pass that converts the fp32 dQ workspace to bf16: no kernel re-reads dK / dV. */
+int mh_attn_bwd_bias(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                     const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, float* bias_grad, int B, int T,
+                     int heads, int causal, float p_drop, uint64_t seed, uint32_t site, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNorm family (module.py:121-123,129-131,232-236: dropout -> +residual -> LayerNorm is

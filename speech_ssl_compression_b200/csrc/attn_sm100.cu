@@ -472,6 +472,7 @@ struct AttnBwdParams {
   DropCfg drop;
   const uint32_t* keep;  // [B, H, keep_words, T] keep bits written by the forward (required when dropout is on)
   int keep_words;
+  float* kv_bias_grad;   // optional f32 [3E]: [E + c] += column sums of dK, [2E + c] += column sums of dV (k / v bias gradients)
   float keep_scale;      // 1 / (1 - p) exactly as the forward applied it
 };
 
@@ -954,6 +955,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
+        if (p.kv_bias_grad != nullptr && w.n_iter > 0) {
+          // k / v bias gradients = column sums of dK / dV over the keys: this warp holds 32 keys (lanes) x 32 columns (16 of
+          // dK, 16 of dV).  Transposing butterfly: after the step with stride s every lane keeps the half of its values whose
+          // column index has bit s set like the lane does -- 31 shuffles, lane l ends with the sum of column l.
+          float v[32];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            v[t] = __uint_as_float(rk[t]);
+            v[16 + t] = __uint_as_float(rv[t]);
+          }
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int t = 0; t < sft; ++t) {
+              const float send = up ? v[t] : v[t + sft];
+              const float keepv = up ? v[t + sft] : v[t];
+              v[t] = keepv + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+          }
+          // lane l: column l of (dK cols part*16 .. +15 | dV cols part*16 .. +15) of head w.h (rows past the sequence end are 0)
+          atomicAdd(p.kv_bias_grad + (lane < 16 ? p.E : 2 * p.E) + w.h * HD + part * 16 + (lane & 15), v[0]);
+        }
         const uint32_t row = smem_u32(sP) + r * 128;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -1000,7 +1024,7 @@ __global__ void dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat16* __
 // Block = 8 warps over a slab of 256 columns and a slice of rows (the layout of norm.cu's colsum_kernel).
 __global__ void __launch_bounds__(256)
 dq_finish_colsum_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ out, int rows, int E,
-                        int rows_per_block) {
+                        int rows_per_block, int sum_cols) {
   pdl_prologue();
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1036,7 +1060,7 @@ dq_finish_colsum_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict_
           }
         }
       }
-    } else {
+    } else if (col0 < sum_cols) {
       const __nv_bfloat16* xp = dqkv + col0;
       int r = r0 + warp;
       for (; r + 24 < r1; r += 32) {
@@ -1063,7 +1087,7 @@ dq_finish_colsum_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict_
   for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
   __syncthreads();
   const int col = blockIdx.x * 256 + threadIdx.x;
-  if (col < cols) {
+  if (col < sum_cols) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
@@ -1076,17 +1100,25 @@ using namespace mh;
 
 // dqkv[:, 0:E] = bf16(dq_acc) and colsum[c] += sum_rows dqkv[:, c] (c < 3E): finishes an mh_attn_bwd_ex call made with
 // flags & 4 and produces the q / k / v bias gradients in the same pass
+static int dq_finish_colsum_launch(const float* dq_acc, void* dqkv, float* colsum, int rows, int E, int sum_cols, void* stream);
+
 extern "C" int mh_dq_finish_colsum(const float* dq_acc, void* dqkv, float* colsum, int rows, int E, void* stream) {
+  return dq_finish_colsum_launch(dq_acc, dqkv, colsum, rows, E, 3 * E, stream);
+}
+
+// sum_cols = 3E: all of q / k / v;  E: only the q columns (the k / v sums came out of the attention backward itself), the grid
+// then covers the dQ slabs only
+static int dq_finish_colsum_launch(const float* dq_acc, void* dqkv, float* colsum, int rows, int E, int sum_cols, void* stream) {
   MH_CHECK(rows > 0 && E > 0 && E % 8 == 0 && dq_acc != nullptr && dqkv != nullptr && colsum != nullptr,
            "dq_finish_colsum: bad arguments (rows %d, E %d)", rows, E);
-  const int cols = 3 * E;
+  const int cols = sum_cols;
   const int gx = (cols + 255) / 256;
   int gy = (sm_count() * 4 + gx - 1) / gx;
   int rpb = (rows + gy - 1) / gy;
   if (rpb < 64) rpb = 64;
   gy = (rows + rpb - 1) / rpb;
   MH_CUDA(launch_pdl(dq_finish_colsum_kernel, dim3(gx, gy), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), dq_acc,
-                     reinterpret_cast<__nv_bfloat16*>(dqkv), colsum, rows, E, rpb));
+                     reinterpret_cast<__nv_bfloat16*>(dqkv), colsum, rows, E, rpb, sum_cols));
   ++g_launches;
   return 0;
 }
@@ -1140,13 +1172,14 @@ extern "C" int mh_attn_trace_read(long long* host_out) {  // debug builds only: 
 
 static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                          const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, bool finish, void* stream);
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, bool finish,
+                         float* bias_grad, void* stream);
 
 extern "C" int mh_attn_bwd(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                            const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
                            int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
   return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site, true,
-                       false, true, stream);
+                       false, true, nullptr, stream);
 }
 
 // flags: 1 = dq_acc has ALREADY been zeroed by the caller (e.g. on a side stream under the preceding GEMMs),
@@ -1156,12 +1189,26 @@ extern "C" int mh_attn_bwd_ex(const void* qkv, const int* kv_len, const void* ou
                               const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
                               int causal, float p_drop, uint64_t seed, uint32_t site, int flags, void* stream) {
   return attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site,
-                       !(flags & 1), (flags & 2) != 0, !(flags & 4), stream);
+                       !(flags & 1), (flags & 2) != 0, !(flags & 4), nullptr, stream);
+}
+
+// mh_attn_bwd_ex (flags 1, 2 as above) plus the q / k / v bias gradients: bias_grad[0:3E] += column sums of dqkv.  The k / v
+// parts are reduced inside the attention backward from the fp32 dK / dV accumulators (no second pass over those 2E columns),
+// the q part in the finishing pass that converts the fp32 dQ workspace to bf16.
+extern "C" int mh_attn_bwd_bias(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
+                                const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, float* bias_grad, int B, int T,
+                                int heads, int causal, float p_drop, uint64_t seed, uint32_t site, int flags, void* stream) {
+  MH_CHECK(bias_grad != nullptr, "attn_bwd_bias: null bias_grad");
+  const int rc = attn_bwd_impl(qkv, kv_len, out, dout, lse, keep_bits, delta, dq_acc, dqkv, B, T, heads, causal, p_drop, seed, site,
+                               !(flags & 1), (flags & 2) != 0, false, bias_grad, stream);
+  if (rc) return rc;
+  return dq_finish_colsum_launch(dq_acc, dqkv, bias_grad, B * T, heads * HD, heads * HD, stream);
 }
 
 static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, const void* dout, const float* lse,
                          const uint8_t* keep_bits, float* delta, float* dq_acc, void* dqkv, int B, int T, int heads,
-                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, bool finish, void* stream) {
+                         int causal, float p_drop, uint64_t seed, uint32_t site, bool zero_dq, bool have_delta, bool finish,
+                         float* bias_grad, void* stream) {
   MH_CHECK(B > 0 && T > 0 && heads > 0, "attn_bwd: bad shape B=%d T=%d heads=%d", B, T, heads);
   MH_CHECK(!(p_drop > 0.f) || keep_bits != nullptr, "attn_bwd: dropout needs the keep bits written by mh_attn_fwd");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1202,6 +1249,7 @@ static int attn_bwd_impl(const void* qkv, const int* kv_len, const void* out, co
   p.keep = reinterpret_cast<const uint32_t*>(keep_bits);
   p.keep_words = ((T + 127) / 128) * 4;
   p.keep_scale = p.drop.scale;
+  p.kv_bias_grad = bias_grad;
   {
     const long long items = static_cast<long long>((T + BKV - 1) / BKV) * heads * B;
     MH_CHECK(items < (1LL << 31), "attn_bwd: too many work items");

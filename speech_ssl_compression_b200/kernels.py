@@ -129,16 +129,23 @@ def attn_bwd(qkv, kv_len, out, dout, lse, keep, B, T, heads, *, causal=False, p_
             raise ValueError("attn_bwd: dq_acc must be a contiguous fp32 workspace of B*T*E elements")
         flags |= 1
     if bias_grad is not None:
-        # ``bias_grad``: fp32 [3E], the stacked q / k / v bias gradients: the bf16 conversion of dQ and the column sums
-        # of dqkv are one pass (mh_dq_finish_colsum) instead of dq_finish + a separate column-sum kernel
+        # ``bias_grad``: fp32 [3E], the stacked q / k / v bias gradients: the k / v parts come out of the attention backward
+        # itself (column sums of its fp32 dK / dV accumulators), the q part out of the pass that converts dQ to bf16
         if bias_grad.dtype != torch.float32 or bias_grad.numel() != 3 * E or not bias_grad.is_contiguous():
             raise ValueError("attn_bwd: bias_grad must be contiguous fp32 [3E]")
-        flags |= 4
+        _call("mh_attn_bwd_bias", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
+              _p(bias_grad), c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site),
+              c_int(flags), _s())
+        return dqkv
     _call("mh_attn_bwd_ex", _p(qkv), _p(kv_len), _p(out), _p(dout), _p(lse), _p(keep), _p(delta), _p(dq_acc), _p(dqkv),
           c_int(B), c_int(T), c_int(heads), c_int(int(causal)), _f(p_drop), c_uint64(seed), c_uint32(site), c_int(flags), _s())
-    if bias_grad is not None:
-        _call("mh_dq_finish_colsum", _p(dq_acc), _p(dqkv), _p(bias_grad), c_int(B * T), c_int(E), _s())
     return dqkv
+
+
+def dq_finish_colsum(dq_acc, dqkv, colsum):
+    """dqkv[:, 0:E] = bf16(dq_acc); colsum[0:3E] += column sums of dqkv (finishes a mh_attn_bwd_ex call made with flags & 4)."""
+    rows, E = dq_acc.shape
+    _call("mh_dq_finish_colsum", _p(dq_acc), _p(dqkv), _p(colsum), c_int(rows), c_int(E), _s())
 
 
 # ------------------------------------------------------------------------------ layer norm

@@ -1,7 +1,7 @@
-// LayerNorm forward / backward and bias-gradient column sums: one warp per row, fp32 statistics,
-// warp-shuffle reductions.  Rows reach a warp through its private 3-deep cp.async ring in shared
-// memory (16-byte chunks, lane-private slots): two rows are in flight while one is reduced and
-// no registers are spent on prefetch.
+// LayerNorm forward / backward and bias-gradient column sums: fp32 statistics, warp-shuffle reductions, packed fp32
+// arithmetic.  Rows reach a warp through its private 3-deep cp.async ring in shared memory (16-byte chunks, lane-private
+// slots): two rows are in flight while one is reduced and no registers are spent on prefetch.  Forward: one warp per row,
+// gamma / beta resident in registers.  Backward: NCH warps per row (one 8-column chunk per lane), see ln_bwd_kernel.
 #include "mh_b200.h"
 #define MH_PDL_FAMILY 4
 #include "mh_common.cuh"
@@ -29,12 +29,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
 constexpr int ln_fwd_smem_bytes(int nch) { return LN_WARPS * LNB_STAGES * nch * 512; }
 
 // NCH = number of 8-element chunks per lane (cols <= NCH * 256); EXACT: cols == NCH * 256, no chunk predicates
-// (the encoder's 768 and 512 columns) -- these kernels are as much issue-bound as HBM-bound, every instruction
-// per element counts.
-// Forward: same ring as the backward.  MEASURED: neutral here (17.9 us per launch inside the step either way).  ncu
-// (profiles/r01_q_ncu_ln_fwd.txt): the output stays in L2, DRAM sees 2 TB/s, issue slots are 33 % busy and 46 % of
-// the stalls are long-scoreboard -- the kernel is bound by the latency chain of one row per warp (load -> two
-// dependent shuffle reductions -> store), not by bandwidth; interleaving two rows per warp is the open lever.
+// (the encoder's 768 and 512 columns).
+// ncu on the first ring version (profiles/r01_q_ncu_ln_fwd.txt, r02 re-capture): L1/TEX throughput 78 %, DRAM 22 % -- 6 of the
+// 10.5 KB a row moved through L1 were gamma / beta reloads.  With them resident the kernel streams at 6 TB/s (12.4 us per
+// launch in the step against 18.1).
 #ifndef LN_FWD_MINB
 #define LN_FWD_MINB 3
 #endif

@@ -43,17 +43,27 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad
 // ------------------------------------------------------------------------------------------------
-constexpr int PCF_NT = 3;                        // 128-row time tiles per CTA
-constexpr int PCF_ROWS = PCF_NT * 128 + 128;     // window rows kept in smem (384 + 127 used)
+// Two taps per MMA.  With one tap per MMA (N = 48) every 128 x 48 x 16 instruction reads 5.5 KB of operands for 24 clk of
+// math: 229 B/clk against the 128 B/clk of shared memory, i.e. ~55 % of the tensor peak by construction.  The A rows of
+// tap 2m (window rows base + 2m + r) multiplied by B = [W_2m | W_2m+1] (N = 96) give D0[r] (the tap-2m term of output row
+// r) and D1[r] = x[base + 2m + r] W_2m+1 -- the tap-(2m+1) term of output row r - 1.  So out[r] = D0[r] + D1[r + 1]:
+// the second accumulator is read one TMEM lane up in the epilogue, a 128-row tile yields 127 output rows, and the A
+// operand traffic per FLOP halves.
+constexpr int PCF_NT = 2;                        // 128-row MMA tiles per CTA
+constexpr int PCF_TSTRIDE = 127;                 // output rows per tile (see above)
+constexpr int PCF_ROWS = 384;                    // window rows kept in smem (127 + 126 + 127 + 1 = 381 used)
 constexpr int PCF_CS = PCF_ROWS * 16;            // chunk stride in bytes
-constexpr int PCF_TPS = 4;                       // taps per weight stage
+constexpr int PCF_TPS = 4;                       // taps per weight stage (= 2 tap pairs)
 constexpr int PCF_STAGES = 3;
+constexpr int PC_PAIR_BYTES = 2 * PC_TAP_BYTES;  // one tap pair of one group: [6 chunks][96 rows = 2 taps x 48 co][8] bf16
 constexpr int PCF_STAGE_BYTES = PCF_TPS * PC_TAP_BYTES;
-constexpr int PCF_SMEM = PC_CHUNKS * PCF_CS + PCF_STAGES * PCF_STAGE_BYTES + 128 + 128 /*align*/;
+constexpr int PCF_XCH_BYTES = 2 * 4 * PC_CG * 4; // D1 rows of the warps' first lanes (lane 31 needs the next warp's lane 0), x2 tiles
+constexpr int PCF_SMEM = PC_CHUNKS * PCF_CS + PCF_STAGES * PCF_STAGE_BYTES + PCF_XCH_BYTES + 128 + 128 /*align*/;
 constexpr int PCF_THREADS = 192;                 // warps 0-3 epilogue, 4 = loads, 5 = MMA
+constexpr int PCF_TMEM_TILE = 96;                // accumulator columns per tile: D0 | D1
 
 struct PosConvParams {
-  const __nv_bfloat16* w;      // [G][128][6][48][8]
+  const __nv_bfloat16* w;      // [G][64 tap pairs][6 chunks][96 = (tap & 1) * 48 + co][8]
   const float* bias;           // [C] or null
   const __nv_bfloat16* res;    // [B*T, C] residual added in the epilogue
   __nv_bfloat16* z;            // [B*T, C] pre-activation output (mode 0) or null
@@ -67,7 +77,8 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sX = smem;
   uint8_t* sW = sX + PC_CHUNKS * PCF_CS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + PCF_STAGES * PCF_STAGE_BYTES);
+  float* sXch = reinterpret_cast<float*>(sW + PCF_STAGES * PCF_STAGE_BYTES);  // [tile][warp][48]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + PCF_XCH_BYTES / 4);
   uint64_t* x_full = bars;
   uint64_t* w_full = bars + 1;                 // [PCF_STAGES]
   uint64_t* w_empty = w_full + PCF_STAGES;     // [PCF_STAGES]
@@ -76,8 +87,8 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
-  const int t0 = slab * (PCF_NT * 128);
-  const int n_tiles = min(PCF_NT, (p.T - t0 + 127) / 128);
+  const int t0 = slab * (PCF_NT * PCF_TSTRIDE);
+  const int n_tiles = min(PCF_NT, (p.T - t0 + PCF_TSTRIDE - 1) / PCF_TSTRIDE);
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -98,7 +109,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
       // per channel chunk; rows outside [0, T) are zero filled by the TMA unit = the conv's zero padding
       mbar_expect_tx(x_full, PC_CHUNKS * PCF_ROWS * 16);
       for (int c = 0; c < PC_CHUNKS; ++c)
-        for (int r0 = 0; r0 < PCF_ROWS; r0 += 256)
+        for (int r0 = 0; r0 < PCF_ROWS; r0 += 128)
           tma_load_3d(sX + c * PCF_CS + r0 * 16, &tmX, x_full, g * PC_CG + c * 8, t0 - p.pad_left + r0, b);
       const uint8_t* wg = reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(g) * PC_TAPS * PC_TAP_BYTES;
       int stage = 0;
@@ -113,7 +124,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
     __syncwarp();
   } else if (warp == 5) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, PC_CG, false, false);
+      const uint32_t idesc = make_idesc_bf16(128, 2 * PC_CG, false, false);
       const uint32_t xa = smem_u32(sX);
       mbar_wait(x_full, 0);
       int stage = 0;
@@ -123,15 +134,15 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
         tc_fence_after();
         const uint32_t wb = smem_u32(sW + stage * PCF_STAGE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < PCF_TPS; ++kk) {
-          const int k = k0 + kk;
+        for (int kk = 0; kk < PCF_TPS / 2; ++kk) {
+          const int k = k0 + 2 * kk;  // even tap of the pair
           for (int i = 0; i < n_tiles; ++i) {
 #pragma unroll
             for (int ks = 0; ks < PC_CG / 16; ++ks) {
-              // A: rows (i*128 + k) .. +127 of chunks 2ks, 2ks+1;  B: 48 weight rows of the same chunks
-              const uint64_t adesc = make_sdesc_ns(xa + (2 * ks) * PCF_CS + (i * 128 + k) * 16, PCF_CS, 128);
-              const uint64_t bdesc = make_sdesc_ns(wb + kk * PC_TAP_BYTES + (2 * ks) * (PC_CG * 16), PC_CG * 16, 128);
-              umma_bf16(tmem_base + i * 64, adesc, bdesc, idesc, (k > 0 || ks > 0) ? 1u : 0u);
+              // A: window rows (i*127 + k) .. +127 of chunks 2ks, 2ks+1;  B: the pair's 96 weight rows of the same chunks
+              const uint64_t adesc = make_sdesc_ns(xa + (2 * ks) * PCF_CS + (i * PCF_TSTRIDE + k) * 16, PCF_CS, 128);
+              const uint64_t bdesc = make_sdesc_ns(wb + kk * PC_PAIR_BYTES + (2 * ks) * (2 * PC_CG * 16), 2 * PC_CG * 16, 128);
+              umma_bf16(tmem_base + i * PCF_TMEM_TILE, adesc, bdesc, idesc, (k > 0 || ks > 0) ? 1u : 0u);
             }
           }
         }
@@ -148,18 +159,42 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
     mbar_wait(acc_full, 0);
     tc_fence_after();
     for (int i = 0; i < n_tiles; ++i) {
-      const int t = t0 + i * 128 + r;
-      uint32_t ra[32], rb[16];
-      tmem_ld32(tmem_base + lane_off + i * 64, ra);
-      tmem_ld16(tmem_base + lane_off + i * 64 + 32, rb);
-      tmem_ld_wait();
-      if (t >= p.T) continue;
+      // D1 (odd taps) belongs to the output row one lane DOWN: fetch this lane's D1 row, hand lane 0's copy to the previous
+      // warp through shared memory (its lane 31 needs it), then shift by one lane
+      uint32_t d1[48];
+      {
+        uint32_t lo[32], hi[16];
+        tmem_ld32(tmem_base + lane_off + i * PCF_TMEM_TILE + PC_CG, lo);
+        tmem_ld16(tmem_base + lane_off + i * PCF_TMEM_TILE + PC_CG + 32, hi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) d1[c] = lo[c];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) d1[32 + c] = hi[c];
+      }
+      float* xch = sXch + (i * 4 + warp) * PC_CG;
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < PC_CG; c += 4)
+          *reinterpret_cast<uint4*>(xch + c) = make_uint4(d1[c], d1[c + 1], d1[c + 2], d1[c + 3]);
+      }
+      bar_sync(1, 128);  // the four epilogue warps (tile i's slots are written once: no second barrier)
+#pragma unroll
+      for (int c = 0; c < PC_CG; ++c) {
+        const uint32_t up = __shfl_down_sync(0xffffffffu, d1[c], 1);
+        d1[c] = (lane == 31 && warp < 3) ? __float_as_uint(xch[PC_CG + c]) : up;  // (row 127 has no successor: not stored)
+      }
+      const int t = t0 + i * PCF_TSTRIDE + r;
+      if (r >= PCF_TSTRIDE || t >= p.T) continue;
       const long long off = (static_cast<long long>(b) * p.T + t) * p.C + g * PC_CG;
 #pragma unroll
       for (int c = 0; c < PC_CHUNKS; ++c) {
+        uint32_t d0[8];
+        tmem_ld8(tmem_base + lane_off + i * PCF_TMEM_TILE + c * 8, d0);
+        tmem_ld_wait();
         float v[8], res[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(c < 4 ? ra[c * 8 + j] : rb[(c - 4) * 8 + j]);
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(d0[j]) + __uint_as_float(d1[c * 8 + j]);
         bf16x8_to_f32(ldg128(p.res + off + c * 8), res);
         if (p.mode == 0) {
           if (p.bias != nullptr) {
@@ -334,7 +369,7 @@ __global__ void pc_normsq_kernel(const float* __restrict__ v, float* __restrict_
   }
   atomicAdd(normsq + k, s);
 }
-// w_fwd[g][k][ci/8][co][ci%8] = s_k v[g*48+co][ci][k];   w_bwd[g][k'][co/8][ci][co%8] = s_k v[g*48+co][ci][k], k = 127 - k'
+// w_fwd[g][k/2][ci/8][(k&1)*48+co][ci%8] = s_k v[g*48+co][ci][k];   w_bwd[g][k'/2][co/8][(k'&1)*48+ci][co%8] = same value, k = 127 - k'
 __global__ void pc_weight_prep_kernel(const float* __restrict__ v, const float* __restrict__ gain,
                                       const float* __restrict__ normsq, __nv_bfloat16* __restrict__ w_fwd,
                                       __nv_bfloat16* __restrict__ w_bwd, float* __restrict__ norm_out, int groups) {
@@ -352,9 +387,12 @@ __global__ void pc_weight_prep_kernel(const float* __restrict__ v, const float* 
   for (int i = threadIdx.x; i < PC_CG * PC_TAPS; i += blockDim.x) {
     const int k = i / PC_CG, ci = i % PC_CG;
     const __nv_bfloat16 w = __float2bfloat16(tile[ci][k]);
-    w_fwd[(((static_cast<size_t>(g) * PC_TAPS + k) * PC_CHUNKS + ci / 8) * PC_CG + co) * 8 + (ci & 7)] = w;
-    if (w_bwd != nullptr)
-      w_bwd[(((static_cast<size_t>(g) * PC_TAPS + (PC_TAPS - 1 - k)) * PC_CHUNKS + co / 8) * PC_CG + ci) * 8 + (co & 7)] = w;
+    // tap-pair layout of posconv_kernel: [g][k / 2][chunk][(k & 1) * 48 + row][8]
+    w_fwd[((((static_cast<size_t>(g) * (PC_TAPS / 2) + k / 2) * PC_CHUNKS + ci / 8) * 2 + (k & 1)) * PC_CG + co) * 8 + (ci & 7)] = w;
+    if (w_bwd != nullptr) {
+      const int kb = PC_TAPS - 1 - k;
+      w_bwd[((((static_cast<size_t>(g) * (PC_TAPS / 2) + kb / 2) * PC_CHUNKS + co / 8) * 2 + (kb & 1)) * PC_CG + ci) * 8 + (co & 7)] = w;
+    }
   }
 }
 // dot[k] = sum_{co,ci} dw * v
@@ -461,7 +499,7 @@ extern "C" int mh_posconv_weight_prep(const float* v, const float* g, void* w_fw
 static int posconv_launch(const void* x, const void* w, const float* bias, const void* res, void* z, void* y, int B, int T,
                           int C, int pad_left, int mode, cudaStream_t st) {
   CUtensorMap tm;
-  int rc = make_tmap_rows(&tm, x, B, T, C, 256);
+  int rc = make_tmap_rows(&tm, x, B, T, C, 128);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -475,7 +513,7 @@ static int posconv_launch(const void* x, const void* w, const float* bias, const
   p.z = reinterpret_cast<__nv_bfloat16*>(z);
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.B = B; p.T = T; p.C = C; p.pad_left = pad_left; p.mode = mode;
-  const int slabs = (T + PCF_NT * 128 - 1) / (PCF_NT * 128);
+  const int slabs = (T + PCF_NT * PCF_TSTRIDE - 1) / (PCF_NT * PCF_TSTRIDE);
   posconv_kernel<<<dim3(slabs, C / PC_CG, B), PCF_THREADS, PCF_SMEM, st>>>(tm, p);
   MH_LAUNCH_CHECK();
   ++g_launches;

@@ -185,13 +185,14 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmX, const PosConvParams p) {
         d1[c] = (lane == 31 && warp < 3) ? __float_as_uint(xch[PC_CG + c]) : up;  // (row 127 has no successor: not stored)
       }
       const int t = t0 + i * PCF_TSTRIDE + r;
-      if (r >= PCF_TSTRIDE || t >= p.T) continue;
-      const long long off = (static_cast<long long>(b) * p.T + t) * p.C + g * PC_CG;
+      const bool valid = r < PCF_TSTRIDE && t < p.T;  // (no early exit: the TMEM loads below are warp-collective)
+      const long long off = (static_cast<long long>(b) * p.T + (valid ? t : 0)) * p.C + g * PC_CG;
 #pragma unroll
       for (int c = 0; c < PC_CHUNKS; ++c) {
         uint32_t d0[8];
         tmem_ld8(tmem_base + lane_off + i * PCF_TMEM_TILE + c * 8, d0);
         tmem_ld_wait();
+        if (!valid) continue;
         float v[8], res[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(d0[j]) + __uint_as_float(d1[c * 8 + j]);
